@@ -1,0 +1,369 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A CPU restatement (torch-CPU tensors, fp32 by default, optional fp64) of the one AdaNeRF hot path
+this repository accelerates:
+
+    rays -> SpherePosDir features -> sampling MLP -> threshold / top-K / compaction
+         -> positional encoding -> shading MLP -> alpha composite
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg
+may import this module, and only as the checker / reported CPU baseline.  The product path
+(`adanerf_b200`) never imports it and has no CPU fallback.
+
+Every function cites the reference lines (relative to /root/reference/) it restates.
+
+PINNING: the reference ships no tests / golden vectors, so this oracle is
+pinned against *outputs of the reference itself run in the build container*:
+`oracle/gen_golden.py` imports the unmodified reference (`oracle/ref_harness.py`), writes
+`tests/golden/*.npz`, and `tests/test_oracle_golden.py` checks this file against those fixtures
+(and, when /root/reference is present, against the live reference on fresh seeds).
+torch version / thread count are recorded inside every golden file.
+"""
+import math
+
+import numpy as np
+import torch
+
+D_CELLS = 128  # multiDepthFeatures (configs/fine_training.ini:11)
+
+# Scene constants of the two exports shipped with the reference
+# (adanerf_real_time_viewer/sample/dataset_info.txt, sample_pavillon_16/dataset_info.txt).
+SCENE_BARBERSHOP = dict(
+    view_cell_center=[2.25, 7.75, 1.5], view_cell_size=[1.5, 1.5, 0.4],
+    depth_range=[-0.42766728550195693, 7.07244257926941], fov=1.5271797180175781,
+    max_depth=8.704841423034669)
+SCENE_PAVILLON = dict(
+    view_cell_center=[0.783, -3.19, 1.39], view_cell_size=[0.7, 0.7, 0.2],
+    depth_range=[0.1542200982570648, 8.358194804191589], fov=1.1386263370513916,
+    max_depth=8.79825210571289)
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 0a: pixel ray directions -- src/util/raygeneration.py:10-26 (float64 numpy, like the ref)
+# ----------------------------------------------------------------------------------------------
+def generate_ray_directions(w, h, fov, focal=None):
+    if focal is None:
+        focal = 0.5 * w / math.tan(0.5 * fov)  # src/datasets.py:181-182
+    x_dist = np.tan(fov / 2) * focal
+    y_dist = x_dist * (h / w)
+    x_pp = x_dist / (w / 2)
+    y_pp = y_dist / (h / 2)
+    xs = -(x_dist - x_pp / 2) + x_pp * np.arange(w, dtype=np.float64)
+    ys = -(y_dist - y_pp / 2) + y_pp * np.arange(h, dtype=np.float64)
+    ray = np.empty((h, w, 3), dtype=np.float64)
+    ray[:, :, 0] = xs[None, :]
+    ray[:, :, 1] = ys[:, None]
+    ray[:, :, 2] = focal
+    dirs = ray / np.linalg.norm(ray, axis=2)[:, :, None]
+    dirs[:, :, 1] *= -1.0
+    dirs[:, :, 2] *= -1.0
+    return dirs  # [h, w, 3] float64; the reference casts to float32 (src/datasets.py:268-269)
+
+
+# ----------------------------------------------------------------------------------------------
+# positional encoding -- src/util/feature_encoding.py:54-73 (encode: :22-23)
+# ----------------------------------------------------------------------------------------------
+def posenc(v, n_freqs):
+    """[., 3] -> [., 3 + 6*n_freqs]: [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(L-1) v), cos(2^(L-1) v)]."""
+    freqs = 2.0 ** torch.linspace(0.0, n_freqs - 1, steps=n_freqs)
+    out = [v]
+    for f in freqs:
+        f = f.to(v.dtype)
+        out.append(torch.sin(v * f))
+        out.append(torch.cos(v * f))
+    return torch.cat(out, -1)
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 0b: SpherePosDir.batch -- src/features.py:845-899, compute_ray_offset :769-791
+# ----------------------------------------------------------------------------------------------
+def stage0_sphere_pos_dir(pose, rot, dirs, scene, n_freq_pos=10, n_freq_dir=4):
+    """pose [3], rot [3,3], dirs [N,3] -> x0 [N,90] (dir block FIRST), ray_o [N,3], ray_d [N,3]."""
+    dt = dirs.dtype
+    c = torch.tensor(scene["view_cell_center"], dtype=torch.float32).to(dt)  # :759 (float32 tensor)
+    # view_cell_radius is a float64 0-dim tensor in the reference (:761); r**2 then promotes like a
+    # python scalar would, i.e. it is rounded to the working dtype when combined with fp32 tensors.
+    r = float(np.linalg.norm(np.array(scene["view_cell_size"]) / 2.0))
+    nds = (rot @ dirs.T).T                                   # :858-859  bmm(rot, dirs^T)^T
+    omc = pose - c                                           # :781
+    u_dot = torch.sum(omc[None, :] * nds, dim=1)             # :784
+    r_t = torch.tensor(r, dtype=torch.float64)
+    c2 = (torch.sum(omc ** 2, dim=-1) - (r_t ** 2).to(dt))   # :786-787
+    delta = u_dot ** 2 - c2
+    t = -u_dot + torch.sqrt(torch.clamp_min(delta, 0))       # :788-790
+    p = pose[None, :] + nds * t[:, None]                     # :863-864
+    enc_d = posenc(nds / torch.norm(nds, dim=-1, keepdim=True), n_freq_dir)   # :866
+    enc_p = posenc(p, n_freq_pos)                            # :867
+    x0 = torch.cat([enc_d, enc_p], -1)                       # :868-871 (dir block first)
+    return x0, p, nds
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 1: BaseNet.forward -- src/models.py:183-195 (no skips for net 0)
+# ----------------------------------------------------------------------------------------------
+def mlp0_forward(x0, sd0):
+    h = x0
+    n_layers = len([k for k in sd0 if k.endswith(".weight")])
+    for i in range(n_layers):
+        h = torch.nn.functional.linear(h, sd0[f"layers.{i}.weight"], sd0[f"layers.{i}.bias"])
+        if i + 1 < n_layers:
+            h = torch.relu(h)
+    return h  # raw0 [N,128]; used RAW (FeatureSet.postprocess is the identity, features.py:68-71)
+
+
+# ----------------------------------------------------------------------------------------------
+# LogTransform.to_world -- src/util/depth_transformations.py:37-48
+# ----------------------------------------------------------------------------------------------
+def log_to_world(z, depth_range):
+    max_v = depth_range[1] - depth_range[0]
+    w = (max_v + 1) ** z
+    w = w - 1.0
+    w = w + depth_range[0]
+    return w
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 2: FromClassifiedDepthAdaptive.generate -- src/nerf_raymarch_common.py:699-757
+# ----------------------------------------------------------------------------------------------
+def stage2_sample(raw0, thr, K, depth_range, z_near=0.001, z_far=1.0):
+    """raw0 [N,128] -> dict(z [N,K] world depth (inf padded, ascending), zp [N,K], cell [N,K] int64
+    (-1 padded), count [N] int64).  Dense path (thr == 0): z [N,K] only, zp = raw0 (features.py:504-505)."""
+    n = raw0.shape[0]
+    if thr == 0.0:                                            # :708-720
+        t_vals = torch.linspace(0.0, 1.0, steps=int(K + 1))[0:-1] + (0.5 / K)
+        t_vals = t_vals.to(raw0.dtype)
+        near = torch.ones((n, 1), dtype=raw0.dtype) * z_near
+        far = torch.ones((n, 1), dtype=raw0.dtype) * z_far
+        z = near * (1.0 - t_vals) + far * t_vals
+        cell = torch.arange(K, dtype=torch.int64)[None, :].expand(n, K)
+        return dict(z=log_to_world(z, depth_range), zp=raw0, cell=cell,
+                    count=torch.full((n,), K, dtype=torch.int64))
+    disc = raw0.shape[1]
+    cell_size = 1.0 / disc
+    # :726 -- the reference calls torch.sort(descending=True) WITHOUT stable=True, so its order among
+    # exactly tied values is implementation-defined (tests/test_oracle_golden.py::test_stage2_stress_vectors);
+    # this oracle and the CUDA path define ties as lower-cell-index-first (stable descending sort).
+    vals, idx = torch.sort(raw0, dim=1, descending=True, stable=True)
+    act = (vals >= thr)                                       # :728-729  (>=, not >)
+    count = act.sum(1)                                        # :732
+    actf = act[:, :K].to(raw0.dtype)
+    z = (actf * idx[:, :K] + actf * 0.5) * cell_size          # :738-742
+    zp = actf * vals[:, :K]                                   # :745
+    empty = count == 0
+    z[empty, 0] = (idx[empty, 0] + 0.5) * cell_size           # :748
+    zp[empty, 0] = vals[empty, 0]                             # :749
+    z[z == 0] = float("inf")                                  # :752
+    z, perm = torch.sort(z, dim=1)                            # :754
+    zp = torch.gather(zp, 1, perm)                            # :755
+    cell = torch.where(torch.isfinite(z), torch.floor(z * disc).to(torch.int64),
+                       torch.full_like(perm, -1))
+    n_r = torch.clamp(count, max=K)
+    n_r = torch.where(empty, torch.ones_like(n_r), n_r)
+    return dict(z=log_to_world(z, depth_range), zp=zp, cell=cell, count=n_r)
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 3: RayMarchFromPoses.batch -- src/features.py:438-484;
+#          normalization_inverse_sqrt_dist_centered -- src/nerf_raymarch_common.py:226-230
+# ----------------------------------------------------------------------------------------------
+def normalize_inverse_sqrt_dist_centered(x, center, max_depth):
+    loc = x - center
+    local = torch.sqrt(torch.linalg.norm(loc, dim=-1))
+    return loc / (math.sqrt(max_depth) * local[..., None])
+
+
+def stage3_encode(ray_o, ray_d, z, scene, compact=True, n_freq_pos=10, n_freq_dir=4):
+    """ray_o, ray_d [N,3]; z [N,K] world depth (inf = dead slot).
+    -> x1 [M,90] (pos block FIRST), mapping [N*K] bool, z_packed [M].  The reference encodes all N*K
+    slots and then masks (features.py:458-484); restated the same way but dead slots are skipped
+    (their values are discarded by the mask and never observed)."""
+    dt = ray_o.dtype
+    n, k = z.shape
+    c = torch.tensor(scene["view_cell_center"], dtype=torch.float32).to(dt)   # features.py:345
+    mapping = (float("inf") > z).flatten() if compact else torch.ones(n * k, dtype=torch.bool)
+    sel = torch.nonzero(mapping).flatten()
+    ray_idx = sel // k
+    zs = z.flatten()[sel]
+    pos = ray_o[ray_idx] + ray_d[ray_idx] * zs[:, None]                       # :458
+    pos = normalize_inverse_sqrt_dist_centered(pos, c, scene["max_depth"])    # :466-467
+    x1 = torch.cat([posenc(pos, n_freq_pos), posenc(ray_d[ray_idx], n_freq_dir)], -1)   # :473-479
+    return x1, mapping, zs
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 4: NeRF.forward -- src/models.py:254-277 (skips=[4], use_viewdirs=True)
+# ----------------------------------------------------------------------------------------------
+def mlp1_forward(x1, sd1, input_ch=63):
+    lin = torch.nn.functional.linear
+    pts, views = x1[:, :input_ch], x1[:, input_ch:]
+    h = pts
+    for i in range(8):
+        h = torch.relu(lin(h, sd1[f"pts_linears.{i}.weight"], sd1[f"pts_linears.{i}.bias"]))
+        if i == 4:
+            h = torch.cat([pts, h], -1)                       # :260-261 (pts first)
+    alpha = lin(h, sd1["alpha_linear.weight"], sd1["alpha_linear.bias"])
+    feat = lin(h, sd1["feature_linear.weight"], sd1["feature_linear.bias"])       # no activation
+    h = torch.cat([feat, views], -1)                          # :266 (feature first)
+    h = torch.relu(lin(h, sd1["views_linears.0.weight"], sd1["views_linears.0.bias"]))
+    rgb = lin(h, sd1["rgb_linear.weight"], sd1["rgb_linear.bias"])
+    return torch.cat([rgb, alpha], -1)                        # [M,4] = [rgb, alpha]
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 5: adaptive_raw2outputs -- src/nerf_raymarch_common.py:91-144 (accumulation_mult "alpha")
+# ----------------------------------------------------------------------------------------------
+def stage5_composite(raw1, z_packed, zp, mapping, n_rays, K):
+    """raw1 [M,4], z_packed [M], zp [N,K], mapping [N*K] bool (or None = dense)
+    -> dict(rgb [N,3], weights [N,K], alpha [N,K], depth_map [N], acc [N])."""
+    s = torch.sigmoid(raw1)                                   # :94
+    if mapping is not None:
+        restored = torch.zeros((n_rays * K, 4), dtype=raw1.dtype)        # :100
+        restored_z = torch.zeros((n_rays * K,), dtype=raw1.dtype)
+        sel = torch.nonzero(mapping).flatten()
+        restored[sel] = s                                     # :105
+        restored_z[sel] = z_packed
+    else:
+        restored, restored_z = s, z_packed
+    restored = restored.view(n_rays, K, 4)
+    restored_z = restored_z.view(n_rays, K)
+    alpha = restored[..., 3] * zp                             # :116,123-125
+    trans = torch.cumprod(torch.cat([torch.ones((n_rays, 1), dtype=raw1.dtype),
+                                     1.0 - alpha + 1e-10], -1), -1)[:, :-1]   # :128-129
+    weights = alpha * trans
+    rgb = torch.sum(weights[..., None] * restored[..., :3], -2)            # :135
+    depth_map = torch.sum(weights * restored_z, -1)           # :137
+    acc = torch.sum(weights, -1)                              # :139
+    return dict(rgb=rgb, weights=weights, alpha=alpha, depth_map=depth_map, acc=acc)
+
+
+# ----------------------------------------------------------------------------------------------
+# glue: TrainConfig.inference -- src/train_data.py:278-299
+# ----------------------------------------------------------------------------------------------
+def render_rays(pose, rot, dirs, sd0, sd1, scene, thr, K, return_stages=False):
+    """One `inference` call of the reference on one batch of rays (all tensors CPU)."""
+    with torch.no_grad():
+        x0, ray_o, ray_d = stage0_sphere_pos_dir(pose, rot, dirs, scene)
+        raw0 = mlp0_forward(x0, sd0)
+        s2 = stage2_sample(raw0, thr, K, scene["depth_range"])
+        n = dirs.shape[0]
+        if thr == 0.0:
+            x1, mapping, zs = stage3_encode(ray_o, ray_d, s2["z"], scene, compact=False)
+            raw1 = mlp1_forward(x1, sd1)
+            comp = stage5_composite(raw1, zs, s2["zp"], None, n, K)
+        else:
+            x1, mapping, zs = stage3_encode(ray_o, ray_d, s2["z"], scene, compact=True)
+            raw1 = mlp1_forward(x1, sd1)
+            comp = stage5_composite(raw1, zs, s2["zp"], mapping, n, K)
+        # AdaptiveSamplePositions := sum_k mapping / K   (features.py:561-563)
+        asp = mapping.view(n, K).sum(1) / K
+    out = dict(rgb=comp["rgb"], n_samples=mapping.view(n, K).sum(1), asp=asp)
+    if return_stages:
+        out.update(x0=x0, ray_o=ray_o, ray_d=ray_d, raw0=raw0, z=s2["z"], zp=s2["zp"], cell=s2["cell"],
+                   count=s2["count"], x1=x1, mapping=mapping, z_packed=zs, raw1=raw1,
+                   weights=comp["weights"], alpha=comp["alpha"], depth_map=comp["depth_map"], acc=comp["acc"])
+    return out
+
+
+def render_frame(pose, rot, dirs, sd0, sd1, scene, thr, K, chunk=8192):
+    """Chunked full-image loop -- src/evaluate.py:216-235 with inferenceChunkSize (configs/*.ini:31)."""
+    rgbs, ns = [], []
+    for b0 in range(0, dirs.shape[0], chunk):
+        o = render_rays(pose, rot, dirs[b0:b0 + chunk], sd0, sd1, scene, thr, K)
+        rgbs.append(o["rgb"])
+        ns.append(o["n_samples"])
+    return torch.cat(rgbs, 0), torch.cat(ns, 0)
+
+
+def psnr(a, b):
+    """src/evaluate.py:49-54: 10 log10(1 / mse)."""
+    mse = float(torch.mean((torch.as_tensor(a, dtype=torch.float64) - torch.as_tensor(b, dtype=torch.float64)) ** 2))
+    return float("inf") if mse == 0 else 10.0 * math.log10(1.0 / mse)
+
+
+# ----------------------------------------------------------------------------------------------
+# weights: same construction order / RNG consumption as BaseNet.__init__ (src/models.py:71-80) and
+# NeRF.__init__ (src/models.py:226-250), so a seed gives the same parameters as the reference.
+# ----------------------------------------------------------------------------------------------
+def init_sampling_net(n_in=90, n_out=128, W=256, D=8):
+    layers = [torch.nn.Linear(n_in, W)]
+    for i in range(1, D):
+        layers.append(torch.nn.Linear(W, W if i != D - 1 else n_out))
+    for l in layers:
+        torch.nn.init.kaiming_normal_(l.weight)
+    sd = {}
+    for i, l in enumerate(layers):
+        sd[f"layers.{i}.weight"] = l.weight.detach().clone()
+        sd[f"layers.{i}.bias"] = l.bias.detach().clone()
+    return sd
+
+
+def init_shading_net(input_ch=63, input_ch_views=27, W=256, D=8, skips=(4,)):
+    pts = [torch.nn.Linear(input_ch, W)] + [
+        torch.nn.Linear(W, W) if i not in skips else torch.nn.Linear(W + input_ch, W) for i in range(D - 1)]
+    views = [torch.nn.Linear(input_ch_views + W, W // 2)]
+    feature = torch.nn.Linear(W, W)
+    alpha = torch.nn.Linear(W, 1)
+    rgb = torch.nn.Linear(W // 2, 3)
+    for l in pts:
+        torch.nn.init.kaiming_normal_(l.weight)
+    for l in views:
+        torch.nn.init.kaiming_normal_(l.weight)
+    sd = {}
+    for i, l in enumerate(pts):
+        sd[f"pts_linears.{i}.weight"] = l.weight.detach().clone()
+        sd[f"pts_linears.{i}.bias"] = l.bias.detach().clone()
+    sd["views_linears.0.weight"] = views[0].weight.detach().clone()
+    sd["views_linears.0.bias"] = views[0].bias.detach().clone()
+    sd["feature_linear.weight"] = feature.weight.detach().clone()
+    sd["feature_linear.bias"] = feature.bias.detach().clone()
+    sd["alpha_linear.weight"] = alpha.weight.detach().clone()
+    sd["alpha_linear.bias"] = alpha.bias.detach().clone()
+    sd["rgb_linear.weight"] = rgb.weight.detach().clone()
+    sd["rgb_linear.bias"] = rgb.bias.detach().clone()
+    return sd
+
+
+def make_weights(kind="shaped", seed=0, thr=0.2, target_spr=8.0):
+    """Synthetic weight sets of SURVEY.md 8(d).
+    'rand'   : reference default init (ModelSelection.getModel order: net 0 then net 1).
+    'shaped' : same seed, then the sampling net's last layer is scaled by 0.15 and its bias shifted so
+               that the mean number of cells >= thr is ~target_spr of 128 on a probe batch, and the
+               shading net's last layers are damped so sigmoid inputs look trained (raw0 is used
+               un-squashed, so plain random init saturates every ray at K and drives alpha*zp out of [0,1])."""
+    torch.manual_seed(seed)
+    sd0 = init_sampling_net()
+    sd1 = init_shading_net()
+    if kind == "rand":
+        return sd0, sd1
+    if kind != "shaped":
+        raise ValueError(kind)
+    sd0["layers.7.weight"] = sd0["layers.7.weight"] * 0.15
+    sd0["layers.7.bias"] = sd0["layers.7.bias"] * 0.15
+    # bisect a constant bias shift on a fixed probe batch (Barbershop geometry, every 157th ray of
+    # the 800x800 grid, camera at the view-cell centre, identity rotation -- the bench configuration)
+    scene = SCENE_BARBERSHOP
+    dirs = torch.from_numpy(generate_ray_directions(800, 800, scene["fov"]).reshape(-1, 3)[::157]).float()
+    pose = torch.tensor(scene["view_cell_center"], dtype=torch.float32)
+    x0, _, _ = stage0_sphere_pos_dir(pose, torch.eye(3), dirs, scene)
+    with torch.no_grad():
+        base = mlp0_forward(x0, sd0)
+    lo, hi = -4.0, 4.0
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        spr = float(((base + mid) >= thr).sum(1).float().mean())
+        if spr > target_spr:
+            hi = mid
+        else:
+            lo = mid
+    sd0["layers.7.bias"] = sd0["layers.7.bias"] + 0.5 * (lo + hi)
+    return sd0, sd1
+
+
+def rotation_yaw(deg):
+    a = math.radians(deg)
+    return torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]],
+                        dtype=torch.float32)
+
+
+def to_dtype(sd, dtype):
+    return {k: v.to(dtype) for k, v in sd.items()}
