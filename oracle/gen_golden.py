@@ -85,6 +85,8 @@ def stage2_stress():
     r = torch.full((128,), -5.0); r[0] = 3.0; rows.append(r)    # single survivor, cell 0
     for _ in range(53):                                          # quantised values => many exact ties
         rows.append(torch.round(torch.rand(128, generator=g) * 8) / 8 - 0.3)
+    for i in range(40):                                          # generic tie-free rows, various spreads
+        rows.append((torch.rand(128, generator=g) - 0.5) * (0.5 + 0.1 * i) + 0.2)
     raw0 = torch.stack(rows).float()
     dr = orc.SCENE_BARBERSHOP["depth_range"]
     arrays = dict(meta=meta(case="stage2_stress", depth_range=dr), raw0=raw0.numpy())

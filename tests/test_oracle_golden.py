@@ -77,13 +77,17 @@ def test_stage2_stress_vectors():
     g = load_golden("stage2_stress")
     raw0 = torch.from_numpy(g["raw0"])
     dr = g["meta"]["depth_range"]
-    has_ties = np.array([len(np.unique(r)) < r.size for r in g["raw0"]])
-    assert (~has_ties).sum() >= 6 and has_ties.sum() >= 20
+    srt = -np.sort(-g["raw0"], axis=1)
     for K in (1, 4, 8, 16, 128):
         for thr in (0.2, 0.5):
             s2 = orc.stage2_sample(raw0, thr, K, dr)
             z, zp = s2["z"].numpy(), s2["zp"].numpy()
             gz, gzp = g[f"z_K{K}_t{thr}"], g[f"zp_K{K}_t{thr}"]
+            cnt = (srt >= np.float32(thr)).sum(1)
+            # a tie only matters at the arg-max fallback or across the K-th/K+1-th boundary
+            has_ties = ((cnt == 0) & (srt[:, 0] == srt[:, 1])) | \
+                       ((cnt > K) & (srt[:, min(K, 127) - 1] == srt[:, min(K, 127)]))
+            assert (~has_ties).sum() >= 45
             np.testing.assert_array_equal(z[~has_ties], gz[~has_ties])
             np.testing.assert_array_equal(zp[~has_ties], gzp[~has_ties])
             np.testing.assert_array_equal(np.isfinite(z).sum(1), np.isfinite(gz).sum(1))
