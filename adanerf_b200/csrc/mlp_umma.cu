@@ -1,0 +1,419 @@
+// tcgen05 / TMEM fused MLP kernel (see mlp_umma.cuh for the design).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "mlp_umma.cuh"
+#include "ptx.cuh"
+
+namespace adn {
+
+template <int NSPLIT>
+struct MlpCfg {
+  static constexpr int kNB = (NSPLIT == 2) ? 4 : 5;            // activation blocks per slot and term
+  static constexpr int kStages = (NSPLIT == 2) ? 3 : 4;        // weight ring depth
+  static constexpr int kStageBytes = NSPLIT * kBlkBytes;       // [128 x 64] hi (+ lo)
+};
+
+template <int NSPLIT, int NG>
+constexpr size_t mlp_smem_layout_bytes() {
+  return size_t(NG) * NSPLIT * MlpCfg<NSPLIT>::kNB * kBlkBytes + size_t(MlpCfg<NSPLIT>::kStages) * MlpCfg<NSPLIT>::kStageBytes +
+         256 /*barriers*/ + 1024 /*alignment slack*/;
+}
+
+size_t mlp_smem_bytes(int nsplit, int ng) {
+  if (nsplit == 2) return mlp_smem_layout_bytes<2, 1>();
+  return ng == 2 ? mlp_smem_layout_bytes<1, 2>() : mlp_smem_layout_bytes<1, 1>();
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Epilogue for 32 consecutive accumulator columns [c, c+32) of one row.
+template <int NSPLIT>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, const MlpLayer& L, const MlpProgram& prog,
+                                               const float* __restrict__ fblob, uint8_t* act_hi, uint8_t* act_lo,
+                                               int row_in_tile, long long grow, long long rows, float* __restrict__ out,
+                                               float& alpha, float (&rgb)[3]) {
+  float v[32];
+  const float4* b4 = reinterpret_cast<const float4*>(fblob + L.bias_off + c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(b4 + j);
+    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+  }
+  if (L.flags & LF_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (L.flags & LF_ALPHA_DOT) {
+    const float4* w4 = reinterpret_cast<const float4*>(fblob + prog.alpha_w_off + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 w = __ldg(w4 + j);
+      alpha = fmaf(v[4 * j + 0], w.x, alpha);
+      alpha = fmaf(v[4 * j + 1], w.y, alpha);
+      alpha = fmaf(v[4 * j + 2], w.z, alpha);
+      alpha = fmaf(v[4 * j + 3], w.w, alpha);
+    }
+  }
+  if (L.flags & LF_OUT_ACT) {
+    // columns [c, c+32) -> block out_blk0 + c/64, 16-byte chunks (c%64)/8 .. +3, XOR-swizzled by row%8
+    const uint32_t blk = L.out_blk0 + (c >> 6);
+    const uint32_t rbase = blk * kBlkBytes + (row_in_tile >> 3) * 1024u + (row_in_tile & 7) * 128u;
+    const uint32_t cc0 = (c & 63) >> 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 hi;
+      hi.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+      hi.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+      hi.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+      hi.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      const uint32_t off = rbase + (((cc0 + q) ^ (row_in_tile & 7)) << 4);
+      *reinterpret_cast<uint4*>(act_hi + off) = hi;
+      if (NSPLIT == 2) {
+        float l[8];
+        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          l[2 * e + 0] = v[8 * q + 2 * e + 0] - __uint_as_float(hw[e] << 16);
+          l[2 * e + 1] = v[8 * q + 2 * e + 1] - __uint_as_float(hw[e] & 0xFFFF0000u);
+        }
+        uint4 lo;
+        lo.x = pack_bf16x2(l[0], l[1]);
+        lo.y = pack_bf16x2(l[2], l[3]);
+        lo.z = pack_bf16x2(l[4], l[5]);
+        lo.w = pack_bf16x2(l[6], l[7]);
+        *reinterpret_cast<uint4*>(act_lo + off) = lo;
+      }
+    }
+  }
+  if (L.flags & LF_FINAL_RAW) {
+    if (grow < rows) {
+      float4* o4 = reinterpret_cast<float4*>(out + grow * prog.out_cols + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  if (L.flags & LF_FINAL_RGB) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4* w4 = reinterpret_cast<const float4*>(fblob + prog.rgb_w_off + k * 128 + c);
+      float acc = rgb[k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w = __ldg(w4 + j);
+        acc = fmaf(v[4 * j + 0], w.x, acc);
+        acc = fmaf(v[4 * j + 1], w.y, acc);
+        acc = fmaf(v[4 * j + 2], w.z, acc);
+        acc = fmaf(v[4 * j + 3], w.w, acc);
+      }
+      rgb[k] = acc;
+    }
+  }
+}
+
+template <int NSPLIT, int NG>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict__ wblob,
+                const float* __restrict__ fblob, const uint8_t* __restrict__ in_tiles, float* __restrict__ out,
+                const long long* __restrict__ rows_dev, long long rows_host, int* err_flag) {
+  using Cfg = MlpCfg<NSPLIT>;
+  constexpr int NB = Cfg::kNB;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGE_BYTES = Cfg::kStageBytes;
+  constexpr int EW = 8 / NG;  // epilogue warps per tile slot
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* act = smem;                                                   // [NG][NSPLIT][NB] blocks
+  uint8_t* ring = act + size_t(NG) * NSPLIT * NB * kBlkBytes;            // [STAGES] stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(STAGES) * STAGE_BYTES);
+  uint64_t* w_full = bars;                 // [STAGES]
+  uint64_t* w_empty = bars + STAGES;       // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;  // [NG]
+  uint64_t* act_ready = acc_full + NG;     // [NG]
+  uint64_t* in_full = act_ready + NG;      // [NG]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + NG);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const long long rows = rows_dev ? *rows_dev : rows_host;
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(&acc_full[g], 1);
+      mbar_init(&act_ready[g], EW);
+      mbar_init(&in_full[g], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto act_ptr = [&](int g, int term, int blk) -> uint8_t* {
+    return act + (size_t(g * NSPLIT + term) * NB + blk) * kBlkBytes;
+  };
+  auto tile_of = [&](long long iter, int g) -> long long {
+    return (iter * gridDim.x + blockIdx.x) * NG + g;
+  };
+
+  if (warp == 0) {
+    // ===================================================================== weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long iter = 0;; ++iter) {
+        if (tile_of(iter, 0) >= n_tiles) break;
+        for (int l = 0; l < prog.n_layers; ++l) {
+          const MlpLayer& L = prog.layers[l];
+          const int n_st = int(L.n_kb) * int(L.n_half);
+          for (int g = 0; g < NG; ++g) {
+            if (tile_of(iter, g) >= n_tiles) continue;
+            const uint8_t* src = wblob + L.w_off;
+            for (int i = 0; i < n_st; ++i) {
+              mbar_wait(&w_empty[stage], phase ^ 1, err_flag, 1);
+              mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+              bulk_g2s(ring + size_t(stage) * STAGE_BYTES, src + size_t(i) * STAGE_BYTES, STAGE_BYTES, &w_full[stage]);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ========================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t in_phase[NG], ar_phase[NG];
+      for (int g = 0; g < NG; ++g) in_phase[g] = ar_phase[g] = 0;
+      for (long long iter = 0;; ++iter) {
+        if (tile_of(iter, 0) >= n_tiles) break;
+        for (int l = 0; l < prog.n_layers; ++l) {
+          const MlpLayer& L = prog.layers[l];
+          for (int g = 0; g < NG; ++g) {
+            if (tile_of(iter, g) >= n_tiles) continue;
+            if (l == 0 || (L.flags & LF_WAIT_IN)) {
+              mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
+              in_phase[g] ^= 1;
+            }
+            mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
+            ar_phase[g] ^= 1;
+            tc_fence_after();
+            for (int kb = 0; kb < L.n_kb; ++kb) {
+              const uint32_t a_hi = smem_u32(act_ptr(g, 0, L.a_blk[kb]));
+              const uint32_t a_lo = (NSPLIT == 2) ? smem_u32(act_ptr(g, NSPLIT - 1, L.a_blk[kb])) : 0u;
+              for (int nh = 0; nh < L.n_half; ++nh) {
+                mbar_wait(&w_full[stage], phase, err_flag, 4);
+                tc_fence_after();
+                const uint32_t b_hi = smem_u32(ring + size_t(stage) * STAGE_BYTES);
+                const uint32_t b_lo = b_hi + kBlkBytes;
+                const uint32_t d = tmem_base + uint32_t(g * 256 + nh * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                  umma_bf16(d, make_desc_sw128(a_hi + k * 32), make_desc_sw128(b_hi + k * 32), idesc, acc);
+                  if (NSPLIT == 2) {
+                    umma_bf16(d, make_desc_sw128(a_lo + k * 32), make_desc_sw128(b_hi + k * 32), idesc, 1u);
+                    umma_bf16(d, make_desc_sw128(a_hi + k * 32), make_desc_sw128(b_lo + k * 32), idesc, 1u);
+                  }
+                }
+                umma_commit(&w_empty[stage]);
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+            umma_commit(&acc_full[g]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================================================================ epilogue
+    const int ew = warp - 2;                       // 0..7
+    const int g = (NG == 2) ? (ew >> 2) : 0;       // tile slot
+    const int e = (NG == 2) ? (ew & 3) : ew;       // index inside the slot's warp set
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int col_half = (NG == 2) ? 0 : (ew >> 2);
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t acc_phase = 0;
+    uint8_t* act_hi = act_ptr(g, 0, 0);
+    uint8_t* act_lo = act_ptr(g, NSPLIT - 1, 0);
+    for (long long iter = 0;; ++iter) {
+      const long long t = tile_of(iter, g);
+      if (t >= n_tiles) break;
+      const long long grow = t * kTileM + row_in_tile;
+      if (e == 0 && lane == 0) {
+        const uint8_t* src = in_tiles + size_t(t) * prog.in_tile_stride;
+        const uint32_t bytes = uint32_t(prog.in0_nblk) * kBlkBytes;
+        mbar_arrive_expect_tx(&in_full[g], bytes * NSPLIT);
+        bulk_g2s(act_ptr(g, 0, prog.in0_blk), src + prog.in0_off, bytes, &in_full[g]);
+        if (NSPLIT == 2) bulk_g2s(act_ptr(g, 1, prog.in0_blk), src + prog.in0_lo_off, bytes, &in_full[g]);
+      }
+      // accumulator columns and activation buffers of this slot are free for layer 0
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&act_ready[g]);
+
+      float alpha = 0.0f;
+      float rgb[3] = {0.0f, 0.0f, 0.0f};
+      for (int l = 0; l < prog.n_layers; ++l) {
+        const MlpLayer& L = prog.layers[l];
+        mbar_wait(&acc_full[g], acc_phase, err_flag, 5);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
+          mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
+          bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
+                   &in_full[g]);
+        }
+        const int n_cols = int(L.n_half) * 128;
+        const int span = (NG == 2) ? n_cols : (n_cols >> 1);
+        const int c0 = col_half * span;
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(g * 256);
+        for (int c = c0; c < c0 + span; c += 64) {
+          uint32_t ra[32], rb[32];
+          tmem_ld32(taddr + c, ra);
+          tmem_ld32(taddr + c + 32, rb);
+          tc_wait_ld();
+          epilogue_chunk<NSPLIT>(ra, c, L, prog, fblob, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+          epilogue_chunk<NSPLIT>(rb, c + 32, L, prog, fblob, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+        }
+        if (L.flags & LF_FINAL_RGB) {
+          if (grow < rows) {
+            const float ab = __ldg(fblob + prog.alpha_b_off);
+            const float b0 = __ldg(fblob + prog.rgb_b_off), b1 = __ldg(fblob + prog.rgb_b_off + 1),
+                        b2 = __ldg(fblob + prog.rgb_b_off + 2);
+            reinterpret_cast<float4*>(out)[grow] = make_float4(rgb[0] + b0, rgb[1] + b1, rgb[2] + b2, alpha + ab);
+          }
+        }
+        if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
+        if (l + 1 < prog.n_layers) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&act_ready[g]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// fp32 feature rows [rows, n_feat] -> packed bf16 (hi / lo) SWIZZLE_128B tile blocks.
+// One thread per (row, block, 16-byte chunk): 8 consecutive source columns.
+__global__ void pack_rows_kernel(const float* __restrict__ x, long long rows_host, const long long* __restrict__ rows_dev,
+                                 int n_feat, const __grid_constant__ InputLayout lay, uint8_t* __restrict__ tiles) {
+  const long long rows = rows_dev ? *rows_dev : rows_host;
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+  const long long total = n_tiles * kTileM * lay.n_blk * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = int(i & 7);
+    const long long rb = i >> 3;
+    const int blk = int(rb % lay.n_blk);
+    const long long row = rb / lay.n_blk;
+    const int r = int(row & (kTileM - 1));
+    const long long t = row >> 7;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = chunk * 8 + j;
+      v[j] = (row < rows && kk < lay.valid[blk]) ? x[row * n_feat + lay.src_col0[blk] + kk] : 0.0f;
+    }
+    uint4 hi;
+    hi.x = pack_bf16x2(v[0], v[1]);
+    hi.y = pack_bf16x2(v[2], v[3]);
+    hi.z = pack_bf16x2(v[4], v[5]);
+    hi.w = pack_bf16x2(v[6], v[7]);
+    const uint32_t off = sw128_offset(uint32_t(r), uint32_t(chunk * 8));
+    uint8_t* tb = tiles + size_t(t) * lay.tile_stride;
+    *reinterpret_cast<uint4*>(tb + lay.dst_off_hi[blk] + off) = hi;
+    if (lay.nsplit == 2) {
+      const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+      float l[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        l[2 * e + 0] = v[2 * e + 0] - __uint_as_float(hw[e] << 16);
+        l[2 * e + 1] = v[2 * e + 1] - __uint_as_float(hw[e] & 0xFFFF0000u);
+      }
+      uint4 lo;
+      lo.x = pack_bf16x2(l[0], l[1]);
+      lo.y = pack_bf16x2(l[2], l[3]);
+      lo.z = pack_bf16x2(l[4], l[5]);
+      lo.w = pack_bf16x2(l[6], l[7]);
+      *reinterpret_cast<uint4*>(tb + lay.dst_off_lo[blk] + off) = lo;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+template <int NSPLIT, int NG>
+static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, const float* fblob, const uint8_t* in_tiles,
+                                float* out, const long long* rows_dev, long long rows_host, int* err_flag, int num_sms,
+                                cudaStream_t stream) {
+  static bool attr_set = false;
+  const size_t smem = mlp_smem_layout_bytes<NSPLIT, NG>();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_umma_kernel<NSPLIT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int grid = num_sms;
+  if (!rows_dev) {
+    const long long n_tiles = (rows_host + kTileM - 1) / kTileM;
+    const long long need = (n_tiles + NG - 1) / NG;
+    if (need < grid) grid = int(need < 1 ? 1 : need);
+  }
+  mlp_umma_kernel<NSPLIT, NG><<<grid, kMlpThreads, smem, stream>>>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host,
+                                                                   err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob, const float* fblob,
+                       const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host, int* err_flag,
+                       int num_sms, cudaStream_t stream) {
+  if (nsplit == 2) return launch_mlp_t<2, 1>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
+  if (ng == 2) return launch_mlp_t<1, 2>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
+  return launch_mlp_t<1, 1>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
+}
+
+cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat, const InputLayout& lay,
+                             uint8_t* tiles, cudaStream_t stream) {
+  long long work = ((rows + kTileM - 1) / kTileM) * kTileM * lay.n_blk * 8;
+  int grid = int((work + 255) / 256);
+  if (grid < 1) grid = 1;
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_rows_kernel<<<grid, 256, 0, stream>>>(x, rows, rows_dev, n_feat, lay, tiles);
+  return cudaGetLastError();
+}
+
+}  // namespace adn

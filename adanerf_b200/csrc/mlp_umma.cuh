@@ -1,0 +1,77 @@
+// Fused multi-layer perceptron on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// One persistent CTA per SM walks 128-row tiles of the batch through ALL layers of the network:
+//   * weights stream layer by layer from L2 into a shared-memory ring with 1-D bulk async copies
+//     (TMA engine, SASS UBLKCP), pre-packed on the host as K-major SWIZZLE_128B tiles,
+//   * activations never leave the SM: the fp32 accumulator lives in TMEM, the epilogue warps read it
+//     with tcgen05.ld, add bias / ReLU, round to bf16 (optionally a hi+lo split) and write the next
+//     layer's A operand straight into swizzled shared memory,
+//   * warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one elected thread), warps 2..9 =
+//     epilogue.  With NG = 2 two tiles ping-pong per CTA (tile A's epilogue overlaps tile B's MMAs).
+//
+// NSPLIT = 2 is the split-precision mode of the sampling network: x = hi + lo (both bf16) for
+// activations and weights and three MMAs per K step (hi*hi + lo*hi + hi*lo), fp32 accumulate --
+// fp32-class accuracy, which the bit-exact threshold decisions downstream need.
+#pragma once
+#include <cstdint>
+
+namespace adn {
+
+constexpr int kTileM = 128;
+constexpr int kBlkBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B block
+constexpr int kMaxLayers = 12;
+constexpr int kMlpThreads = 320;  // 10 warps
+
+enum : uint8_t {
+  LF_RELU = 1,
+  LF_ALPHA_DOT = 2,      // accumulate alpha = <post-activation row, alpha_w> on CUDA cores (fp32)
+  LF_OUT_ACT = 4,        // write bf16 activations for the next layer
+  LF_FINAL_RAW = 8,      // write fp32 rows to global (sampling net output / test programs)
+  LF_FINAL_RGB = 16,     // rgb_linear on CUDA cores + write float4 (rgb, alpha)
+  LF_LOAD_IN1_AFTER = 32,  // once this layer's MMAs are done, fetch the 2nd input block (view dirs)
+  LF_WAIT_IN = 64          // the MMA warp must wait for that 2nd input before this layer
+};
+
+struct MlpLayer {
+  uint32_t w_off;     // byte offset of this layer's packed weight stages (consumption order)
+  uint32_t bias_off;  // float offset of the bias vector in the fp32 side blob
+  uint8_t n_kb;       // number of 64-wide K blocks
+  uint8_t a_blk[5];   // activation block index per K block
+  uint8_t n_half;     // N / 128  (1 or 2)
+  uint8_t flags;
+  uint8_t out_blk0;   // first activation block the epilogue writes
+  uint8_t pad[3];
+};
+
+struct MlpProgram {
+  int32_t n_layers;
+  int32_t in0_blk, in0_nblk;  // tile-start input: destination block, number of blocks (per term)
+  int32_t in1_blk;            // 2nd input destination block
+  uint32_t in_tile_stride;    // bytes per tile in the packed input buffer
+  uint32_t in0_off, in0_lo_off, in1_off;
+  uint32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;  // float offsets in the side blob
+  int32_t out_cols;           // row stride of the FINAL_RAW output
+  MlpLayer layers[kMaxLayers];
+};
+
+// Describes how fp32 feature rows map onto the packed bf16 input blocks of a tile.
+struct InputLayout {
+  int32_t n_blk;
+  int32_t src_col0[4];
+  int32_t valid[4];
+  uint32_t dst_off_hi[4];
+  uint32_t dst_off_lo[4];
+  uint32_t tile_stride;
+  int32_t nsplit;
+};
+
+size_t mlp_smem_bytes(int nsplit, int ng);
+
+// Launchers (defined in mlp_umma.cu).  rows_dev may be null (then rows_host is used).
+cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob, const float* fblob,
+                       const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host,
+                       int* err_flag, int num_sms, cudaStream_t stream);
+cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat,
+                             const InputLayout& lay, uint8_t* tiles, cudaStream_t stream);
+
+}  // namespace adn

@@ -1,0 +1,633 @@
+// SIMT stages (see stages.cuh).  All position math uses explicit round-to-nearest intrinsics in the
+// reference's operation order so results track the PyTorch fp32 path (no FMA contraction where torch
+// has separate mul/add; an FMA chain where ATen's K=3 bmm uses one).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "mlp_umma.cuh"
+#include "ptx.cuh"
+#include "stages.cuh"
+
+namespace adn {
+
+constexpr int kNFreqPos = 10;
+constexpr int kNFreqDir = 4;
+constexpr int kFeat = 90;
+
+__device__ __forceinline__ uint32_t bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// enc_L(v) = [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(L-1) v), cos(2^(L-1) v)], each term a 3-vector
+// (src/util/feature_encoding.py:60-73).  Writes 3 + 6L floats.
+template <int L>
+__device__ __forceinline__ void posenc3(const float (&v)[3], float* out) {
+  out[0] = v[0];
+  out[1] = v[1];
+  out[2] = v[2];
+#pragma unroll
+  for (int f = 0; f < L; ++f) {
+    const float freq = float(1 << f);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float s, c;
+      sincosf(__fmul_rn(v[a], freq), &s, &c);
+      out[3 + 6 * f + a] = s;
+      out[3 + 6 * f + 3 + a] = c;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ stage 0a
+__device__ __forceinline__ void pixel_dir(const CameraRays& cam, long long ray, float (&d)[3]) {
+  const int y = cam.row0 + int(ray / cam.W);
+  const int x = int(ray % cam.W);
+  const double rx = __dadd_rn(cam.start_x, __dmul_rn(cam.x_pp, double(x)));
+  const double ry = __dadd_rn(cam.start_y, __dmul_rn(cam.y_pp, double(y)));
+  const double rz = cam.focal;
+  const double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)));
+  d[0] = float(__ddiv_rn(rx, n));
+  d[1] = float(-__ddiv_rn(ry, n));
+  d[2] = float(-__ddiv_rn(rz, n));
+}
+
+__global__ void gen_dirs_kernel(const __grid_constant__ CameraRays cam, long long n_rays, float* __restrict__ dirs) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_rays) return;
+  float d[3];
+  pixel_dir(cam, i, d);
+  dirs[3 * i + 0] = d[0];
+  dirs[3 * i + 1] = d[1];
+  dirs[3 * i + 2] = d[2];
+}
+
+cudaError_t launch_gen_dirs(const CameraRays& cam, long long n_rays, float* d_dirs, cudaStream_t s) {
+  if (n_rays <= 0) return cudaSuccess;
+  gen_dirs_kernel<<<unsigned((n_rays + 255) / 256), 256, 0, s>>>(cam, n_rays, d_dirs);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ stage 0b
+// SpherePosDir.batch (src/features.py:845-899): one thread per ray.
+template <bool FROM_CAMERA>
+__global__ void __launch_bounds__(128)
+stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseDev pd, const float* __restrict__ dirs,
+              const __grid_constant__ CameraRays cam, long long n_rays, float* __restrict__ x0, float* __restrict__ ray_o,
+              float* __restrict__ ray_d, uint8_t* __restrict__ tiles0) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long n_pad = ((n_rays + kTileM - 1) / kTileM) * kTileM;
+  if (i >= n_pad) return;
+  float f[128];
+#pragma unroll
+  for (int j = 0; j < 128; ++j) f[j] = 0.0f;
+  if (i < n_rays) {
+    float d[3];
+    if (FROM_CAMERA) {
+      pixel_dir(cam, i, d);
+    } else {
+      d[0] = dirs[3 * i + 0];
+      d[1] = dirs[3 * i + 1];
+      d[2] = dirs[3 * i + 2];
+    }
+    // nds = R * d : ATen bmm with K = 3 accumulates as an FMA chain over k = 0,1,2 (:858-859)
+    float nds[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      nds[r] = __fmaf_rn(pd.rot[3 * r + 2], d[2], __fmaf_rn(pd.rot[3 * r + 1], d[1], __fmul_rn(pd.rot[3 * r + 0], d[0])));
+    // compute_ray_offset (:769-791)
+    float omc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) omc[a] = __fsub_rn(pd.pose[a], sc.c[a]);
+    const float udot = __fadd_rn(__fadd_rn(__fmul_rn(omc[0], nds[0]), __fmul_rn(omc[1], nds[1])), __fmul_rn(omc[2], nds[2]));
+    const float omc2 = __fadd_rn(__fadd_rn(__fmul_rn(omc[0], omc[0]), __fmul_rn(omc[1], omc[1])), __fmul_rn(omc[2], omc[2]));
+    const float delta = __fsub_rn(__fmul_rn(udot, udot), __fsub_rn(omc2, sc.r2));
+    const float t = __fadd_rn(-udot, __fsqrt_rn(fmaxf(delta, 0.0f)));
+    float p[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(pd.pose[a], __fmul_rn(nds[a], t));
+    const float nn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nds[0], nds[0]), __fmul_rn(nds[1], nds[1])), __fmul_rn(nds[2], nds[2])));
+    float dn[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) dn[a] = __fdiv_rn(nds[a], nn);
+    posenc3<kNFreqDir>(dn, f);                     // 27: direction block FIRST (:868)
+    posenc3<kNFreqPos>(p, f + 3 + 6 * kNFreqDir);  // 63
+    if (ray_o) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ray_o[3 * i + a] = p[a];
+        ray_d[3 * i + a] = nds[a];
+      }
+    }
+    if (x0) {
+#pragma unroll
+      for (int j = 0; j < kFeat; ++j) x0[i * kFeat + j] = f[j];
+    }
+  }
+  if (tiles0) {
+    // packed MLP0 input: per tile [hi blk0 | hi blk1 | lo blk0 | lo blk1], 16 KB each
+    const long long t = i >> 7;
+    const uint32_t r = uint32_t(i & 127);
+    uint8_t* tb = tiles0 + size_t(t) * (4 * kBlkBytes);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float* v = f + b * 64 + ch * 8;
+        uint4 hi;
+        hi.x = bf16x2(v[0], v[1]);
+        hi.y = bf16x2(v[2], v[3]);
+        hi.z = bf16x2(v[4], v[5]);
+        hi.w = bf16x2(v[6], v[7]);
+        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+        uint4 lo;
+        uint32_t lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float l0 = v[2 * e + 0] - __uint_as_float(hw[e] << 16);
+          const float l1 = v[2 * e + 1] - __uint_as_float(hw[e] & 0xFFFF0000u);
+          lw[e] = bf16x2(l0, l1);
+        }
+        lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        const uint32_t off = sw128_offset(r, uint32_t(ch * 8));
+        *reinterpret_cast<uint4*>(tb + b * kBlkBytes + off) = hi;
+        *reinterpret_cast<uint4*>(tb + (2 + b) * kBlkBytes + off) = lo;
+      }
+    }
+  }
+}
+
+cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_dirs, const CameraRays* cam,
+                          long long n_rays, float* d_x0, float* d_ray_o, float* d_ray_d, uint8_t* d_tiles0,
+                          cudaStream_t s) {
+  if (n_rays <= 0) return cudaSuccess;
+  const long long n_pad = ((n_rays + kTileM - 1) / kTileM) * kTileM;
+  const unsigned grid = unsigned((n_pad + 127) / 128);
+  CameraRays c{};
+  if (cam) {
+    c = *cam;
+    stage0_kernel<true><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
+  } else {
+    stage0_kernel<false><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------- stage 2
+// FromClassifiedDepthAdaptive.generate (src/nerf_raymarch_common.py:699-757) + mask compaction
+// (src/features.py:445-446,481-484), single pass:
+//   * one warp per ray, lane l owns cells 4l..4l+3 (one coalesced 512-byte row load),
+//   * survivors = cells >= thr; more than K survivors -> K rounds of warp arg-max (value descending,
+//     ties lower cell first); none -> the arg-max cell; order inside a ray = ascending cell = ascending z,
+//   * per-CTA exclusive scan of the counts + decoupled look-back across CTAs (dynamic tickets), so the
+//     packed order is deterministic ray-major (the torch boolean-mask order) with no host sync.
+constexpr int kS2Rays = 64;     // rays per CTA
+constexpr int kS2Threads = 256;  // 8 warps x 8 rays
+
+struct ValIdx {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool better(const ValIdx& a, const ValIdx& b) {  // a precedes b in sort order
+  return (a.v > b.v) || (a.v == b.v && a.i < b.i);
+}
+__device__ __forceinline__ ValIdx warp_best(ValIdx x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ValIdx y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    if (better(y, x)) x = y;
+  }
+  return x;
+}
+
+// Returns the 4 selection masks (bit l of sel[j] <-> cell 4l+j) and the count, warp uniform.
+__device__ __forceinline__ int select_cells(const float4 v4, float thr, int K, int lane, uint32_t (&sel)[4]) {
+  const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  uint32_t act[4];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    act[j] = __ballot_sync(0xffffffffu, v[j] >= thr);
+    cnt += __popc(act[j]);
+  }
+  if (cnt == 0) {
+    ValIdx b{-INFINITY, 1 << 20};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ValIdx c{v[j], 4 * lane + j};
+      if (better(c, b)) b = c;
+    }
+    b = warp_best(b);
+    const int cell = (b.i < 128) ? b.i : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sel[j] = ((cell & 3) == j) ? (1u << (cell >> 2)) : 0u;
+    return 1;
+  }
+  if (cnt <= K) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sel[j] = act[j];
+    return cnt;
+  }
+  uint32_t mine = 0;  // bit j: my cell j is still a candidate
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mine |= ((act[j] >> lane) & 1u) << j;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sel[j] = 0;
+  for (int round = 0; round < K; ++round) {
+    ValIdx b{-INFINITY, 1 << 20};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((mine >> j) & 1u) {
+        ValIdx c{v[j], 4 * lane + j};
+        if (better(c, b)) b = c;
+      }
+    }
+    b = warp_best(b);
+    const int cell = b.i;
+    if ((cell >> 2) == lane) mine &= ~(1u << (cell & 3));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((cell & 3) == j) sel[j] |= 1u << (cell >> 2);
+  }
+  return K;
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kS2Threads)
+stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K, const float* __restrict__ zlut,
+              int32_t* __restrict__ count, int32_t* __restrict__ offset, int32_t* __restrict__ cell_out,
+              int32_t* __restrict__ ray_out, float* __restrict__ z_out, float* __restrict__ zp_out,
+              long long* __restrict__ total, unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
+              int n_tiles) {
+  __shared__ uint32_t s_sel[kS2Rays][4];
+  __shared__ int s_cnt[kS2Rays];
+  __shared__ int s_off[kS2Rays];
+  __shared__ long long s_prefix;
+  __shared__ int s_tile;
+  __shared__ int s_tile_total;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_tile = int(atomicAdd(ticket, 1u));
+  __syncthreads();
+  const int tile = s_tile;
+  const long long ray0 = (long long)tile * kS2Rays;
+
+  // phase 1: selection
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int rl = warp * 8 + i;
+    const long long r = ray0 + rl;
+    int cnt = 0;
+    uint32_t sel[4] = {0, 0, 0, 0};
+    if (r < n_rays) {
+      const float4 v4 = __ldg(reinterpret_cast<const float4*>(raw0 + r * 128) + lane);
+      cnt = select_cells(v4, thr, K, lane, sel);
+    }
+    if (lane == 0) {
+      s_cnt[rl] = cnt;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_sel[rl][j] = sel[j];
+    }
+  }
+  __syncthreads();
+
+  // CTA scan + decoupled look-back (warp 0)
+  if (warp == 0) {
+    const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+    int x = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    const int excl = x - (a + b);
+    s_off[2 * lane] = excl;
+    s_off[2 * lane + 1] = excl + a;
+    const int tile_total = __shfl_sync(0xffffffffu, x, 31);
+    const unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
+    long long prefix = 0;
+    if (tile > 0) {
+      if (lane == 0) {
+        atomicExch(&tile_state[tile], FLAG_AGG | (unsigned long long)tile_total);
+      }
+      int idx = tile - 1;
+      const long long t0 = clock64();
+      while (true) {
+        const int my = idx - lane;
+        unsigned long long st = FLAG_INC;  // virtual predecessor of tile 0: inclusive prefix 0
+        if (my >= 0) {
+          st = ld_volatile_u64(&tile_state[my]);
+        }
+        const uint32_t ready = __ballot_sync(0xffffffffu, (st >> 62) != 0);
+        const uint32_t inc = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+        // lanes [0, first_inc] must all be ready
+        const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+        const uint32_t need = (first_inc >= 31) ? 0xffffffffu : ((2u << first_inc) - 1u);
+        if ((ready & need) != need) {
+          if (clock64() - t0 > ADN_WATCHDOG_CYCLES) asm volatile("trap;");
+          continue;  // spin
+        }
+        long long contrib = (lane <= first_inc) ? (long long)(st & VMASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        prefix += contrib;
+        if (first_inc < 32) break;
+        idx -= 32;
+      }
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&tile_state[tile], FLAG_INC | (unsigned long long)(prefix + tile_total));
+      s_prefix = prefix;
+      s_tile_total = tile_total;
+      if (tile == n_tiles - 1) *total = prefix + tile_total;
+    }
+  }
+  __syncthreads();
+  const long long prefix = s_prefix;
+
+  // phase 2: write the packed samples (ray-major, ascending cell)
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int rl = warp * 8 + i;
+    const long long r = ray0 + rl;
+    if (r >= n_rays) break;
+    const float4 v4 = __ldg(reinterpret_cast<const float4*>(raw0 + r * 128) + lane);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const long long off = prefix + s_off[rl];
+    if (lane == 0) {
+      count[r] = s_cnt[rl];
+      offset[r] = int32_t(off);
+    }
+    const uint32_t below = (1u << lane) - 1u;
+    int rank = 0;
+    uint32_t sel[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sel[j] = s_sel[rl][j];
+      rank += __popc(sel[j] & below);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((sel[j] >> lane) & 1u) {
+        const int cell = 4 * lane + j;
+        const long long o = off + rank;
+        z_out[o] = zlut[cell];
+        zp_out[o] = v[j];
+        if (cell_out) cell_out[o] = cell;
+        ray_out[o] = int32_t(r);
+        ++rank;
+      }
+    }
+  }
+}
+
+size_t stage2_scratch_bytes(long long n_rays) {
+  const long long n_tiles = (n_rays + kS2Rays - 1) / kS2Rays;
+  return size_t(n_tiles + 2) * 8;
+}
+
+cudaError_t launch_stage2(const float* d_raw0, long long n_rays, float thr, int K, const float* d_zlut, int32_t* d_count,
+                          int32_t* d_offset, int32_t* d_cell, int32_t* d_ray, float* d_z, float* d_zp, long long* d_total,
+                          void* d_scratch, cudaStream_t s) {
+  if (n_rays <= 0) return cudaMemsetAsync(d_total, 0, sizeof(long long), s);
+  const int n_tiles = int((n_rays + kS2Rays - 1) / kS2Rays);
+  cudaError_t e = cudaMemsetAsync(d_scratch, 0, stage2_scratch_bytes(n_rays), s);
+  if (e != cudaSuccess) return e;
+  unsigned long long* state = reinterpret_cast<unsigned long long*>(d_scratch);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(state + n_tiles);
+  stage2_kernel<<<n_tiles, kS2Threads, 0, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray, d_z, d_zp,
+                                               d_total, state, ticket, n_tiles);
+  return cudaGetLastError();
+}
+
+__global__ void stage2_dense_kernel(long long n_rays, int K, int32_t* __restrict__ count, int32_t* __restrict__ offset,
+                                    long long* __restrict__ total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i == 0) *total = n_rays * K;
+  if (i >= n_rays) return;
+  if (count) count[i] = K;
+  if (offset) offset[i] = int32_t(i * K);
+}
+
+cudaError_t launch_stage2_dense(long long n_rays, int K, int32_t* d_count, int32_t* d_offset, long long* d_total,
+                                cudaStream_t s) {
+  const long long n = n_rays > 0 ? n_rays : 1;
+  stage2_dense_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(n_rays, K, d_count, d_offset, d_total);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------- stage 3
+// RayMarchFromPoses.batch (src/features.py:458-479): one thread per packed sample.
+__global__ void __launch_bounds__(128)
+stage3_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ ray_o, const float* __restrict__ ray_d,
+              const int32_t* __restrict__ ray_idx, const float* __restrict__ z, const float* __restrict__ zlut_dense, int K,
+              long long n_samples_host, const long long* __restrict__ n_samples_dev, float* __restrict__ x1,
+              uint8_t* __restrict__ tiles1) {
+  const long long n_samples = n_samples_dev ? *n_samples_dev : n_samples_host;
+  const long long n_pad = ((n_samples + kTileM - 1) / kTileM) * kTileM;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pad; i += (long long)gridDim.x * blockDim.x) {
+    float f[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) f[j] = 0.0f;
+    if (i < n_samples) {
+      long long r;
+      float zw;
+      if (ray_idx) {
+        r = ray_idx[i];
+        zw = z[i];
+      } else {
+        r = i / K;
+        zw = zlut_dense[i - r * K];
+      }
+      float o[3], d[3], pos[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        o[a] = __ldg(ray_o + 3 * r + a);
+        d[a] = __ldg(ray_d + 3 * r + a);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pos[a] = __fsub_rn(__fadd_rn(o[a], __fmul_rn(d[a], zw)), sc.c[a]);   // :458, loc = pos - c
+      // normalization_inverse_sqrt_dist_centered (src/nerf_raymarch_common.py:226-230)
+      const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(pos[0], pos[0]), __fmul_rn(pos[1], pos[1])), __fmul_rn(pos[2], pos[2])));
+      const float den = __fmul_rn(sc.sqrt_max_depth, __fsqrt_rn(nrm));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pos[a] = __fdiv_rn(pos[a], den);
+      posenc3<kNFreqPos>(pos, f);                      // 63: position block FIRST (:473-479)
+      posenc3<kNFreqDir>(d, f + 64);                   // 27 (un-renormalised nds), staged at column 64
+      if (x1) {
+#pragma unroll
+        for (int j = 0; j < 63; ++j) x1[i * kFeat + j] = f[j];
+#pragma unroll
+        for (int j = 0; j < 27; ++j) x1[i * kFeat + 63 + j] = f[64 + j];
+      }
+    }
+    if (tiles1) {
+      // packed MLP1 input: per tile [P: 63 pos features + 0 | V: 27 dir features + zeros], 16 KB each
+      const long long t = i >> 7;
+      const uint32_t r = uint32_t(i & 127);
+      uint8_t* tb = tiles1 + size_t(t) * (2 * kBlkBytes);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const float* v = f + b * 64 + ch * 8;
+          uint4 hi;
+          hi.x = bf16x2(v[0], v[1]);
+          hi.y = bf16x2(v[2], v[3]);
+          hi.z = bf16x2(v[4], v[5]);
+          hi.w = bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(tb + b * kBlkBytes + sw128_offset(r, uint32_t(ch * 8))) = hi;
+        }
+      }
+    }
+  }
+}
+
+cudaError_t launch_stage3(const SceneDev& sc, const float* d_ray_o, const float* d_ray_d, const int32_t* d_ray,
+                          const float* d_z, const float* d_zlut_dense, int K, long long n_samples, const long long* d_total,
+                          float* d_x1, uint8_t* d_tiles1, cudaStream_t s) {
+  // n_samples is an upper bound (capacity) when d_total is given
+  if (n_samples <= 0) return cudaSuccess;
+  long long blocks = (n_samples + kTileM - 1) / kTileM;
+  const long long cap = 148ll * 64;
+  if (d_total && blocks > cap) blocks = cap;   // grid-stride when the true count lives on the device
+  stage3_kernel<<<unsigned(blocks), 128, 0, s>>>(sc, d_ray_o, d_ray_d, d_ray, d_z, d_zlut_dense, K, n_samples, d_total, d_x1,
+                                                 d_tiles1);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------- stage 5
+// adaptive_raw2outputs (src/nerf_raymarch_common.py:91-144), accumulation_mult == "alpha".
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ uint32_t to_rgba8(float r, float g, float b) {
+  // adaptive_cuda_kernels.cu:846-851: clamp to [0,1] * 255, alpha = 255
+  const uint32_t R = uint32_t(fminf(fmaxf(r, 0.0f), 1.0f) * 255.0f);
+  const uint32_t G = uint32_t(fminf(fmaxf(g, 0.0f), 1.0f) * 255.0f);
+  const uint32_t B = uint32_t(fminf(fmaxf(b, 0.0f), 1.0f) * 255.0f);
+  return R | (G << 8) | (B << 16) | (255u << 24);
+}
+
+// One thread per ray, samples visited in order: the same sequential cumprod / sum order as torch.
+__global__ void __launch_bounds__(128)
+stage5_thread_kernel(const float4* __restrict__ raw1, const float* __restrict__ zp, const float* __restrict__ z,
+                     const int32_t* __restrict__ offset, const int32_t* __restrict__ count, long long n_rays, int K,
+                     float* __restrict__ rgb, uint32_t* __restrict__ rgba8, float* __restrict__ weights,
+                     float* __restrict__ depth_map) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const long long off = offset[r];
+  const int n = count[r];
+  float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, dm = 0.0f;
+  for (int j = 0; j < n; ++j) {
+    const float4 q = __ldg(raw1 + off + j);
+    const float sr = sigmoidf_acc(q.x), sg = sigmoidf_acc(q.y), sb = sigmoidf_acc(q.z), sa = sigmoidf_acc(q.w);
+    const float alpha = __fmul_rn(sa, __ldg(zp + off + j));                       // :123-125
+    const float w = __fmul_rn(alpha, T);                                          // :128-129
+    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+    cr = __fadd_rn(cr, __fmul_rn(w, sr));                                         // :135
+    cg = __fadd_rn(cg, __fmul_rn(w, sg));
+    cb = __fadd_rn(cb, __fmul_rn(w, sb));
+    if (depth_map) dm = __fadd_rn(dm, __fmul_rn(w, __ldg(z + off + j)));          // :137
+    if (weights) weights[r * K + j] = w;
+  }
+  if (weights)
+    for (int j = n; j < K; ++j) weights[r * K + j] = 0.0f;
+  if (rgb) {
+    rgb[3 * r + 0] = cr;
+    rgb[3 * r + 1] = cg;
+    rgb[3 * r + 2] = cb;
+  }
+  if (rgba8) rgba8[r] = to_rgba8(cr, cg, cb);
+  if (depth_map) depth_map[r] = dm;
+}
+
+// One warp per ray (dense 128 samples / large K): lanes own consecutive samples, transmittance by a
+// warp-wide product scan with a running carry.
+__global__ void __launch_bounds__(256)
+stage5_warp_kernel(const float4* __restrict__ raw1, const float* __restrict__ zp, const float* __restrict__ z,
+                   const float* __restrict__ zlut_dense, const int32_t* __restrict__ offset,
+                   const int32_t* __restrict__ count, long long n_rays, int K, int dense, float* __restrict__ rgb,
+                   uint32_t* __restrict__ rgba8, float* __restrict__ weights, float* __restrict__ depth_map) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rays) return;
+  const long long off = dense ? r * K : (long long)offset[r];
+  const int n = dense ? K : count[r];
+  float carry = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, dm = 0.0f;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + lane;
+    float alpha = 0.0f, sr = 0.0f, sg = 0.0f, sb = 0.0f, zz = 0.0f;
+    if (j < n) {
+      const float4 q = __ldg(raw1 + off + j);
+      sr = sigmoidf_acc(q.x);
+      sg = sigmoidf_acc(q.y);
+      sb = sigmoidf_acc(q.z);
+      alpha = __fmul_rn(sigmoidf_acc(q.w), __ldg(zp + off + j));
+      if (depth_map) zz = dense ? __ldg(zlut_dense + j) : __ldg(z + off + j);
+    }
+    float f = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    // inclusive product scan
+    float p = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float y = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) p = __fmul_rn(p, y);
+    }
+    float excl = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = __fmul_rn(carry, excl);
+    const float w = __fmul_rn(alpha, T);
+    carry = __fmul_rn(carry, __shfl_sync(0xffffffffu, p, 31));
+    cr = __fadd_rn(cr, __fmul_rn(w, sr));
+    cg = __fadd_rn(cg, __fmul_rn(w, sg));
+    cb = __fadd_rn(cb, __fmul_rn(w, sb));
+    dm = __fadd_rn(dm, __fmul_rn(w, zz));
+    if (weights && j < K) weights[r * K + j] = (j < n) ? w : 0.0f;
+  }
+  if (weights)
+    for (int j = ((n + 31) & ~31) + lane; j < K; j += 32) weights[r * K + j] = 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cr += __shfl_xor_sync(0xffffffffu, cr, o);
+    cg += __shfl_xor_sync(0xffffffffu, cg, o);
+    cb += __shfl_xor_sync(0xffffffffu, cb, o);
+    dm += __shfl_xor_sync(0xffffffffu, dm, o);
+  }
+  if (lane == 0) {
+    if (rgb) {
+      rgb[3 * r + 0] = cr;
+      rgb[3 * r + 1] = cg;
+      rgb[3 * r + 2] = cb;
+    }
+    if (rgba8) rgba8[r] = to_rgba8(cr, cg, cb);
+    if (depth_map) depth_map[r] = dm;
+  }
+}
+
+cudaError_t launch_stage5(const float* d_raw1, const float* d_zp, const float* d_z, const float* d_zlut_dense,
+                          const int32_t* d_offset, const int32_t* d_count, long long n_rays, int K, int dense, float* d_rgb,
+                          uint8_t* d_rgba8, float* d_weights, float* d_depth_map, cudaStream_t s) {
+  if (n_rays <= 0) return cudaSuccess;
+  const float4* raw = reinterpret_cast<const float4*>(d_raw1);
+  uint32_t* rgba = reinterpret_cast<uint32_t*>(d_rgba8);
+  if (dense || K > 32) {
+    const long long threads = n_rays * 32;
+    stage5_warp_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(raw, d_zp, d_z, d_zlut_dense, d_offset, d_count, n_rays,
+                                                                        K, dense, d_rgb, rgba, d_weights, d_depth_map);
+  } else {
+    stage5_thread_kernel<<<unsigned((n_rays + 127) / 128), 128, 0, s>>>(raw, d_zp, d_z, d_offset, d_count, n_rays, K, d_rgb,
+                                                                         rgba, d_weights, d_depth_map);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace adn

@@ -1,0 +1,53 @@
+// SIMT stages of the AdaNeRF hot path (HBM-bound byte/index work): ray generation, SpherePosDir
+// features (stage 0), threshold / top-K / scan compaction (stage 2), positional encoding (stage 3),
+// per-ray transmittance scan + composite (stage 5).  Launchers only; kernels in stages.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace adn {
+
+struct SceneDev {
+  float c[3];          // view_cell_center (fp32, features.py:759 / :345)
+  float r2;            // float(view_cell_radius**2) (features.py:761,786)
+  float sqrt_max_depth;  // float(math.sqrt(max_depth)) (nerf_raymarch_common.py:229)
+  int n_freq_pos, n_freq_dir;
+};
+
+struct CameraRays {  // src/util/raygeneration.py:10-26 in double precision
+  double start_x, start_y, focal, x_pp, y_pp;
+  int W, H, row0;
+};
+
+struct PoseDev {
+  float pose[3];
+  float rot[9];
+};
+
+// Packed-tile destinations (nullptr = skip): MLP0 input tiles (hi/lo) and MLP1 input tiles.
+cudaError_t launch_gen_dirs(const CameraRays& cam, long long n_rays, float* d_dirs, cudaStream_t s);
+cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_dirs, const CameraRays* cam,
+                          long long n_rays, float* d_x0, float* d_ray_o, float* d_ray_d, uint8_t* d_tiles0,
+                          cudaStream_t s);
+
+// Stage 2.  tile_state: [n_ctas + 2] uint64 scratch zeroed by the launcher (memsetAsync).
+size_t stage2_scratch_bytes(long long n_rays);
+cudaError_t launch_stage2(const float* d_raw0, long long n_rays, float thr, int K, const float* d_zlut,
+                          int32_t* d_count, int32_t* d_offset, int32_t* d_cell, int32_t* d_ray, float* d_z, float* d_zp,
+                          long long* d_total, void* d_scratch, cudaStream_t s);
+// Dense (thr == 0): count = K, offset = ray*K, total = N*K; no index arrays are materialised.
+cudaError_t launch_stage2_dense(long long n_rays, int K, int32_t* d_count, int32_t* d_offset, long long* d_total,
+                                cudaStream_t s);
+
+// Stage 3.  Adaptive: sample s -> (d_ray[s], d_z[s]).  Dense (d_ray == nullptr): ray = s / K,
+// z = d_zlut_dense[s % K].  n_samples read from d_total when non-null.
+cudaError_t launch_stage3(const SceneDev& sc, const float* d_ray_o, const float* d_ray_d, const int32_t* d_ray,
+                          const float* d_z, const float* d_zlut_dense, int K, long long n_samples, const long long* d_total,
+                          float* d_x1, uint8_t* d_tiles1, cudaStream_t s);
+
+// Stage 5.  zp: adaptive -> packed [M]; dense (dense_zp_stride > 0) -> raw0 [N, stride].
+cudaError_t launch_stage5(const float* d_raw1, const float* d_zp, const float* d_z, const float* d_zlut_dense,
+                          const int32_t* d_offset, const int32_t* d_count, long long n_rays, int K, int dense,
+                          float* d_rgb, uint8_t* d_rgba8, float* d_weights, float* d_depth_map, cudaStream_t s);
+
+}  // namespace adn

@@ -1,0 +1,261 @@
+"""Python host side of the B200 renderer: mirrors the call surface of the reference's
+`TrainConfig.inference` (src/train_data.py:278-299) as `render(rays, sampling_net, shading_net,
+adaptiveSamplingThreshold)` on top of the C ABI.  PyTorch is used only for device memory and streams."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AdnError, Scene, Stats, TensorDesc
+
+
+def make_scene(view_cell_center, view_cell_size, depth_range, max_depth, fov, z_near=0.001, z_far=1.0,
+               n_freq_pos=10, n_freq_dir=4, **_):
+    s = Scene()
+    s.view_cell_center[:] = [float(x) for x in view_cell_center]
+    s.view_cell_size[:] = [float(x) for x in view_cell_size]
+    s.depth_range[:] = [float(x) for x in depth_range]
+    s.max_depth, s.fov, s.z_near, s.z_far = float(max_depth), float(fov), float(z_near), float(z_far)
+    s.n_freq_pos, s.n_freq_dir = int(n_freq_pos), int(n_freq_dir)
+    return s
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _state_dict_of(net):
+    if hasattr(net, "state_dict"):
+        net = net.state_dict()
+    return {k: np.ascontiguousarray(v.detach().cpu().float().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, np.float32))
+            for k, v in net.items()}
+
+
+class Renderer:
+    """One context per device.  `sampling_net` / `shading_net`: nn.Module or state_dict with the
+    reference's parameter names (src/models.py:71-76, :226-244)."""
+
+    def __init__(self, scene, device=0, sampling_net=None, shading_net=None, _handle=None):
+        self.lib = _lib.load_library()
+        self.device = int(device)
+        self.handle = C.c_void_p()
+        if _handle is not None:
+            self.handle = _handle
+        else:
+            sc = scene if isinstance(scene, Scene) else make_scene(**scene)
+            self._check(self.lib.adn_create(C.byref(self.handle), C.byref(sc), self.device), create=True)
+        if sampling_net is not None:
+            self.set_weights(0, sampling_net)
+        if shading_net is not None:
+            self.set_weights(1, shading_net)
+
+    @classmethod
+    def from_export_dir(cls, path, device=0):
+        """Loads the reference's export directory (src/export.py:28-93). Returns (renderer, thr, K)."""
+        lib = _lib.load_library()
+        h, thr, k = C.c_void_p(), C.c_float(), C.c_int()
+        st = lib.adn_create_from_export_dir(C.byref(h), str(path).encode(), int(device), C.byref(thr), C.byref(k))
+        if st != 0:
+            raise AdnError(st, f"loading export dir {path}")
+        return cls(None, device=device, _handle=h), float(thr.value), int(k.value)
+
+    def _check(self, st, create=False):
+        if st != 0:
+            detail = "" if create or not self.handle else (self.lib.adn_last_error(self.handle) or b"").decode()
+            raise AdnError(st, detail)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.adn_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights / options ---------------------------------------------------------------
+    def set_weights(self, net_id, net):
+        sd = _state_dict_of(net)
+        descs = (TensorDesc * len(sd))()
+        keep = []
+        for i, (k, v) in enumerate(sd.items()):
+            v2 = v.reshape(v.shape[0], -1) if v.ndim >= 1 else v.reshape(1, 1)
+            keep.append((k.encode(), v2))
+            descs[i].name = keep[-1][0]
+            descs[i].data = _fptr(v2)
+            descs[i].rows, descs[i].cols = v2.shape[0], v2.shape[1]
+        self._check(self.lib.adn_set_weights(self.handle, int(net_id), descs, len(sd)))
+
+    def set_option(self, name, value):
+        self._check(self.lib.adn_set_option(self.handle, name.encode(), int(value)))
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.adn_get_stats(self.handle, C.byref(s)))
+        return dict(n_rays=s.n_rays, n_samples=s.n_samples, ms_stage=list(s.ms_stage), kernel_launches=s.kernel_launches)
+
+    # ---- helpers -------------------------------------------------------------------------
+    def _dev(self):
+        return torch.device("cuda", self.device)
+
+    @staticmethod
+    def _pose_rot(pose, rot):
+        p = np.ascontiguousarray(np.asarray(pose.detach().cpu() if isinstance(pose, torch.Tensor) else pose, dtype=np.float32).reshape(3))
+        r = np.ascontiguousarray(np.asarray(rot.detach().cpu() if isinstance(rot, torch.Tensor) else rot, dtype=np.float32).reshape(9))
+        return p, r
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _f32(self, t):
+        t = t.to(device=self._dev(), dtype=torch.float32)
+        return t if t.is_contiguous() else t.contiguous()
+
+    # ---- the hot path --------------------------------------------------------------------
+    def render_rays(self, pose, rot, dirs, thr, K, want_nsamples=True, want_oracle_weights=False):
+        """dirs [N,3] (cuda tensor) -> dict(rgb [N,3], n_samples [N] int32, oracle_weights [N,128])."""
+        p, r = self._pose_rot(pose, rot)
+        d = self._f32(dirs).reshape(-1, 3)
+        n = d.shape[0]
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
+        ns = torch.empty((n,), dtype=torch.int32, device=self._dev()) if want_nsamples else None
+        ow = torch.empty((n, 128), dtype=torch.float32, device=self._dev()) if want_oracle_weights else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.adn_render_rays(self.handle, _fptr(p), _fptr(r), d.data_ptr(), n, float(thr), int(K),
+                                                 rgb.data_ptr(), ns.data_ptr() if ns is not None else None,
+                                                 ow.data_ptr() if ow is not None else None, self._stream()))
+        return dict(rgb=rgb, n_samples=ns, oracle_weights=ow)
+
+    def render_camera(self, pose, rot, W, H, thr, K, row0=0, rows=None, out=None, want_nsamples=False):
+        """Renders image rows [row0, row0+rows) of a WxH pinhole frame; rays generated on the device."""
+        rows = H - row0 if rows is None else rows
+        p, r = self._pose_rot(pose, rot)
+        n = rows * W
+        rgb = out if out is not None else torch.empty((n, 3), dtype=torch.float32, device=self._dev())
+        ns = torch.empty((n,), dtype=torch.int32, device=self._dev()) if want_nsamples else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.adn_render_camera(self.handle, _fptr(p), _fptr(r), W, H, row0, rows, float(thr), int(K),
+                                                   rgb.data_ptr(), ns.data_ptr() if ns is not None else None, self._stream()))
+        return dict(rgb=rgb, n_samples=ns)
+
+    def render_camera_rgba8(self, pose, rot, W, H, thr, K, row0=0, rows=None):
+        rows = H - row0 if rows is None else rows
+        p, r = self._pose_rot(pose, rot)
+        out = torch.empty((rows * W, 4), dtype=torch.uint8, device=self._dev())
+        with torch.cuda.device(self.device):
+            self._check(self.lib.adn_render_camera_rgba8(self.handle, _fptr(p), _fptr(r), W, H, row0, rows, float(thr), int(K),
+                                                         out.data_ptr(), self._stream()))
+        return out
+
+    def render_rays_host(self, pose, rot, dirs_np, thr, K, want_nsamples=True):
+        """Host buffers in, host buffers out (H2D / D2H inside the call)."""
+        p, r = self._pose_rot(pose, rot)
+        d = np.ascontiguousarray(dirs_np, dtype=np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        rgb = np.empty((n, 3), dtype=np.float32)
+        ns = np.empty((n,), dtype=np.int32) if want_nsamples else None
+        self._check(self.lib.adn_render_rays_host(self.handle, _fptr(p), _fptr(r), d.ctypes.data, n, float(thr), int(K),
+                                                  rgb.ctypes.data, ns.ctypes.data if ns is not None else None))
+        return dict(rgb=rgb, n_samples=ns)
+
+    def render_camera_host(self, pose, rot, W, H, thr, K, row0=0, rows=None, out=None, want_nsamples=False):
+        rows = H - row0 if rows is None else rows
+        p, r = self._pose_rot(pose, rot)
+        n = rows * W
+        rgb = out if out is not None else np.empty((n, 3), dtype=np.float32)
+        ns = np.empty((n,), dtype=np.int32) if want_nsamples else None
+        self._check(self.lib.adn_render_camera_host(self.handle, _fptr(p), _fptr(r), W, H, row0, rows, float(thr), int(K),
+                                                    rgb.ctypes.data, ns.ctypes.data if ns is not None else None))
+        return dict(rgb=rgb, n_samples=ns)
+
+    # ---- stage-level entry points (parity tests) --------------------------------------------
+    def generate_ray_directions(self, W, H, row0=0, rows=None):
+        rows = H - row0 if rows is None else rows
+        out = torch.empty((rows * W, 3), dtype=torch.float32, device=self._dev())
+        self._check(self.lib.adn_generate_ray_directions(self.handle, W, H, row0, rows, out.data_ptr(), self._stream()))
+        return out
+
+    def stage0(self, pose, rot, dirs):
+        p, r = self._pose_rot(pose, rot)
+        d = self._f32(dirs).reshape(-1, 3)
+        n = d.shape[0]
+        x0 = torch.empty((n, 90), dtype=torch.float32, device=self._dev())
+        ro = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
+        rd = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
+        self._check(self.lib.adn_stage0_features(self.handle, _fptr(p), _fptr(r), d.data_ptr(), n, x0.data_ptr(),
+                                                 ro.data_ptr(), rd.data_ptr(), self._stream()))
+        return x0, ro, rd
+
+    def mlp0(self, x0, n_out=128):
+        x = self._f32(x0)
+        out = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=self._dev())
+        self._check(self.lib.adn_mlp0_forward(self.handle, x.data_ptr(), x.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def stage2(self, raw0, thr, K):
+        x = self._f32(raw0)
+        n = x.shape[0]
+        dev = self._dev()
+        count = torch.empty((n,), dtype=torch.int32, device=dev)
+        offset = torch.empty((n,), dtype=torch.int32, device=dev)
+        cap = max(n * K, 1)
+        cell = torch.full((cap,), -1, dtype=torch.int32, device=dev)
+        ray = torch.full((cap,), -1, dtype=torch.int32, device=dev)
+        z = torch.full((cap,), float("nan"), dtype=torch.float32, device=dev)
+        zp = torch.full((cap,), float("nan"), dtype=torch.float32, device=dev)
+        total = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self._check(self.lib.adn_stage2_sample(self.handle, x.data_ptr(), n, float(thr), int(K), count.data_ptr(), offset.data_ptr(),
+                                               cell.data_ptr(), ray.data_ptr(), z.data_ptr(), zp.data_ptr(), total.data_ptr(),
+                                               self._stream()))
+        m = int(total.item())
+        return dict(count=count, offset=offset, cell=cell[:m], ray=ray[:m], z=z[:m], zp=zp[:m], total=m)
+
+    def stage3(self, ray_o, ray_d, ray_idx, z):
+        ro, rd, zz = self._f32(ray_o), self._f32(ray_d), self._f32(z)
+        ri = ray_idx.to(device=self._dev(), dtype=torch.int32).contiguous()
+        m = zz.shape[0]
+        x1 = torch.empty((m, 90), dtype=torch.float32, device=self._dev())
+        self._check(self.lib.adn_stage3_encode(self.handle, ro.data_ptr(), rd.data_ptr(), ri.data_ptr(), zz.data_ptr(), m,
+                                               x1.data_ptr(), self._stream()))
+        return x1
+
+    def mlp1(self, x1):
+        x = self._f32(x1)
+        out = torch.empty((x.shape[0], 4), dtype=torch.float32, device=self._dev())
+        self._check(self.lib.adn_mlp1_forward(self.handle, x.data_ptr(), x.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def stage5(self, raw1, zp, z, offset, count, K, want_aux=True):
+        r1, zpp, zz = self._f32(raw1), self._f32(zp), self._f32(z)
+        off = offset.to(device=self._dev(), dtype=torch.int32).contiguous()
+        cnt = count.to(device=self._dev(), dtype=torch.int32).contiguous()
+        n = cnt.shape[0]
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
+        w = torch.empty((n, K), dtype=torch.float32, device=self._dev()) if want_aux else None
+        dm = torch.empty((n,), dtype=torch.float32, device=self._dev()) if want_aux else None
+        self._check(self.lib.adn_stage5_composite(self.handle, r1.data_ptr(), zpp.data_ptr(), zz.data_ptr(), off.data_ptr(),
+                                                  cnt.data_ptr(), n, int(K), rgb.data_ptr(),
+                                                  w.data_ptr() if w is not None else None,
+                                                  dm.data_ptr() if dm is not None else None, self._stream()))
+        return dict(rgb=rgb, weights=w, depth_map=dm)
+
+
+_RENDERERS = {}
+
+
+def render(rays, sampling_net, shading_net, adaptiveSamplingThreshold, *, K, scene, device=0):
+    """The public entry named by BASELINE.json.  `rays` = dict(pose [3], rot [3,3], dirs [N,3]) -- the
+    three tensors `TrainConfig.inference` reads from its batch (ImagePose, ImageRotation,
+    RayDirectionsSamples; src/features.py:832-834).  Returns (rgb [N,3], n_samples [N])."""
+    key = (id(sampling_net), id(shading_net), device, tuple(sorted((k, str(v)) for k, v in scene.items())))
+    r = _RENDERERS.get(key)
+    if r is None:
+        r = Renderer(scene, device=device, sampling_net=sampling_net, shading_net=shading_net)
+        _RENDERERS.clear()
+        _RENDERERS[key] = r
+    out = r.render_rays(rays["pose"], rays["rot"], rays["dirs"], adaptiveSamplingThreshold, K)
+    return out["rgb"], out["n_samples"]

@@ -1,0 +1,358 @@
+"""GPU parity tests: every CUDA stage is driven through the C ABI (ctypes) and compared with the
+golden fixtures produced by the unmodified reference and with the CPU oracle on the same inputs.
+Tolerances (stated per test) follow SURVEY.md 8(d): integer / index work bit-exact, fp32 SIMT stages
+~1e-6 (5e-4 on the 2^9 posenc band), MLPs by their reduced-precision budget, end-to-end by PSNR."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import case_weights, load_golden
+from oracle import adanerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["pav_k8_t0.2", "pav_k8_t0.5", "pav_k16_t0.15", "shaped_k8_t0.2", "rand_k8_t0.2"]
+
+
+def _renderer(scene, sd0=None, sd1=None):
+    from adanerf_b200 import Renderer
+    return Renderer(scene, device=0, sampling_net=sd0, shading_net=sd1)
+
+
+@pytest.fixture(scope="module")
+def bare():
+    r = _renderer(orc.SCENE_BARBERSHOP)
+    yield r
+    r.close()
+
+
+def _packed_from_golden(g, K):
+    """Packed (ray-major, depth-ascending) views of the NaN/zero padded golden tensors."""
+    z = g["z_nan"]
+    mask = np.isfinite(z)
+    ray = np.repeat(np.arange(z.shape[0]), K).reshape(z.shape)[mask]
+    return mask, ray, z[mask]
+
+
+# ------------------------------------------------------------------------------- tcgen05 bring-up
+@pytest.mark.parametrize("n_out", [128, 256])
+@pytest.mark.parametrize("terms", [3, 1])
+def test_umma_single_layer(bare, n_out, terms):
+    """One Linear layer through the tcgen05 path == validates descriptors, swizzle, TMEM loads."""
+    g = torch.Generator().manual_seed(5)
+    W = torch.randn(n_out, 90, generator=g) * 0.3
+    b = torch.randn(n_out, generator=g) * 0.1
+    x = torch.randn(300, 90, generator=g)
+    bare.set_option("mlp0_terms", terms)
+    bare.set_weights(0, {"layers.0.weight": W, "layers.0.bias": b})
+    out = bare.mlp0(x.cuda(), n_out=n_out).cpu()
+    ref = (x.double() @ W.double().T + b.double()).float()
+    err = (out - ref).abs().max().item()
+    print(f"single layer n_out={n_out} terms={terms}: max abs err {err:.3e}")
+    assert err < (2e-5 if terms == 3 else 6e-2)
+    bare.set_option("mlp0_terms", 3)
+
+
+@pytest.mark.parametrize("depth", [2, 3, 8])
+def test_umma_multi_layer(bare, depth):
+    g = torch.Generator().manual_seed(depth)
+    sd = {}
+    dims = [90] + [256] * (depth - 1) + [128]
+    for i in range(depth):
+        sd[f"layers.{i}.weight"] = torch.randn(dims[i + 1], dims[i], generator=g) * (1.4 / dims[i] ** 0.5)
+        sd[f"layers.{i}.bias"] = torch.randn(dims[i + 1], generator=g) * 0.1
+    x = torch.randn(1000, 90, generator=g)
+    bare.set_weights(0, sd)
+    out = bare.mlp0(x.cuda()).cpu()
+    ref = orc.mlp0_forward(x.double(), orc.to_dtype(sd, torch.float64)).float()
+    err = (out - ref).abs().max().item()
+    print(f"depth {depth}: max abs err {err:.3e} (ref scale {ref.abs().max():.2f})")
+    assert err < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------ stage 0
+def test_generate_ray_directions_bit_exact(bare):
+    W, H = 800, 800
+    d = bare.generate_ray_directions(W, H, row0=0, rows=H).cpu().numpy()
+    ref = orc.generate_ray_directions(W, H, orc.SCENE_BARBERSHOP["fov"]).reshape(-1, 3).astype(np.float32)
+    np.testing.assert_array_equal(d, ref)
+    band = bare.generate_ray_directions(W, H, row0=300, rows=7).cpu().numpy()
+    np.testing.assert_array_equal(band, ref[300 * W:307 * W])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_stage0_matches_reference(case):
+    g = load_golden(case)
+    r = _renderer(g["meta"]["scene_params"])
+    x0, ro, rd = r.stage0(g["pose"], g["rot"], torch.from_numpy(g["dirs"]).cuda())
+    np.testing.assert_array_equal(rd.cpu().numpy(), g["ray_d"])                  # FMA chain of ATen bmm
+    np.testing.assert_allclose(ro.cpu().numpy(), g["ray_o"], rtol=0, atol=1e-6)
+    x0 = x0.cpu().numpy()
+    np.testing.assert_allclose(x0[:, :27], g["x0"][:, :27], rtol=0, atol=2e-6)    # direction block
+    # position block: frequency 2^k amplifies a 1-ulp position difference by 2^k
+    err = np.abs(x0[:, 27:] - g["x0"][:, 27:])
+    assert err.max() < 5e-4, err.max()
+    assert err[:, :3 + 6 * 4].max() < 2e-5
+    r.close()
+
+
+# ------------------------------------------------------------------------------------ stage 1
+@pytest.mark.parametrize("case", ["pav_k8_t0.2", "shaped_k8_t0.2", "rand_k8_t0.2"])
+def test_mlp0_matches_reference(case):
+    g = load_golden(case)
+    sd0, _ = case_weights(case)
+    r = _renderer(g["meta"]["scene_params"], sd0=sd0)
+    raw0 = r.mlp0(torch.from_numpy(g["x0"]).cuda()).cpu().numpy()
+    ref64 = orc.mlp0_forward(torch.from_numpy(g["x0"]).double(), orc.to_dtype(sd0, torch.float64)).numpy()
+    scale = max(1.0, np.abs(g["raw0"]).max())
+    err_ref = np.abs(raw0 - g["raw0"]).max() / scale
+    err64 = np.abs(raw0 - ref64).max() / scale
+    noise = np.abs(g["raw0"] - ref64).max() / scale          # the fp32 reference's own distance to fp64
+    flips = ((raw0 >= g["meta"]["thr"]) != (g["raw0"] >= g["meta"]["thr"])).mean()
+    print(f"{case}: |ours-ref|={err_ref:.2e} |ours-f64|={err64:.2e} |ref-f64|={noise:.2e} threshold flips={flips:.2e}")
+    assert err64 < 5e-5, "split-precision sampling MLP must be fp32-class"
+    assert flips < 2e-4
+    r.close()
+
+
+# ------------------------------------------------------------------------------------ stage 2
+@pytest.mark.parametrize("case", CASES)
+def test_stage2_bit_exact_on_reference_raw0(case, bare):
+    g = load_golden(case)
+    m = g["meta"]
+    K = m["K"]
+    r = _renderer(m["scene_params"])
+    s2 = r.stage2(torch.from_numpy(g["raw0"]).cuda(), m["thr"], K)
+    mask, ray, z = _packed_from_golden(g, K)
+    cnt = mask.sum(1)
+    np.testing.assert_array_equal(s2["count"].cpu().numpy(), cnt)
+    np.testing.assert_array_equal(s2["offset"].cpu().numpy(), np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+    assert s2["total"] == cnt.sum()
+    np.testing.assert_array_equal(s2["ray"].cpu().numpy(), ray)
+    # cell ids: invert the golden z through the oracle's cell table
+    o2 = orc.stage2_sample(torch.from_numpy(g["raw0"]), m["thr"], K, m["scene_params"]["depth_range"])
+    np.testing.assert_array_equal(s2["cell"].cpu().numpy(), o2["cell"].numpy()[mask])
+    np.testing.assert_array_equal(s2["zp"].cpu().numpy(), o2["zp"].numpy()[mask])
+    np.testing.assert_allclose(s2["z"].cpu().numpy(), z, rtol=2.5e-7, atol=1e-7)   # pow: <= 1-2 ulp
+    r.close()
+
+
+def test_stage2_stress_vectors(bare):
+    """Ties, all-equal rows, value == thr, nothing above thr ... against the oracle (ties lower-cell-first)."""
+    g = load_golden("stage2_stress")
+    raw0 = torch.from_numpy(g["raw0"])
+    dr = g["meta"]["depth_range"]
+    for K in (1, 4, 8, 16, 128):
+        for thr in (0.2, 0.5):
+            s2 = bare.stage2(raw0.cuda(), thr, K)
+            o2 = orc.stage2_sample(raw0, thr, K, dr)
+            mask = torch.isfinite(o2["z"]).numpy()
+            np.testing.assert_array_equal(s2["count"].cpu().numpy(), o2["count"].numpy())
+            np.testing.assert_array_equal(s2["cell"].cpu().numpy(), o2["cell"].numpy()[mask])
+            np.testing.assert_array_equal(s2["zp"].cpu().numpy(), o2["zp"].numpy()[mask])
+
+
+def test_stage2_large_properties(bare):
+    """Full-frame size: offsets are the exclusive scan of counts, packed rays sorted, cells ascending
+    inside a ray, deterministic across runs; empty and ragged inputs."""
+    g = torch.Generator().manual_seed(3)
+    n = 640000
+    raw0 = (torch.rand(n, 128, generator=g) * 1.2 - 0.8).cuda()
+    a = bare.stage2(raw0, 0.2, 8)
+    b = bare.stage2(raw0, 0.2, 8)
+    cnt = a["count"].long()
+    assert int(cnt.min()) >= 1 and int(cnt.max()) <= 8
+    assert torch.equal(a["offset"].long(), torch.cumsum(cnt, 0) - cnt)
+    assert a["total"] == int(cnt.sum())
+    for k in ("count", "offset", "cell", "ray", "z", "zp"):
+        assert torch.equal(a[k], b[k]), k
+    ray = a["ray"].long()
+    assert bool((ray[1:] >= ray[:-1]).all())
+    same = ray[1:] == ray[:-1]
+    assert bool((a["cell"][1:][same] > a["cell"][:-1][same]).all())
+    vals = raw0[ray, a["cell"].long()]
+    assert torch.equal(vals, a["zp"])
+    e = bare.stage2(raw0[:0], 0.2, 8)
+    assert e["total"] == 0
+    one = bare.stage2(raw0[:1], 0.2, 8)
+    assert one["total"] == int(one["count"][0])
+
+
+# ------------------------------------------------------------------------------------ stage 3
+@pytest.mark.parametrize("case", ["pav_k8_t0.2", "shaped_k8_t0.2"])
+def test_stage3_matches_reference(case):
+    g = load_golden(case)
+    m = g["meta"]
+    K = m["K"]
+    r = _renderer(m["scene_params"])
+    mask, ray, z = _packed_from_golden(g, K)
+    x1 = r.stage3(torch.from_numpy(g["ray_o"]), torch.from_numpy(g["ray_d"]), torch.from_numpy(ray.astype(np.int32)),
+                  torch.from_numpy(z)).cpu().numpy()
+    ref = g["x1_nan"].reshape(-1, 90)[mask.flatten()]
+    err = np.abs(x1 - ref)
+    assert err[:, 63:].max() < 2e-6                 # direction block
+    assert err[:, :3 + 6 * 4].max() < 2e-5          # low position bands
+    assert err.max() < 5e-4, err.max()              # 2^9 band
+    r.close()
+
+
+# ------------------------------------------------------------------------------------ stage 4
+@pytest.mark.parametrize("case", ["pav_k8_t0.2", "shaped_k8_t0.2"])
+def test_mlp1_matches_reference(case):
+    g = load_golden(case)
+    m = g["meta"]
+    _, sd1 = case_weights(case)
+    r = _renderer(m["scene_params"], sd1=sd1)
+    mask, _, _ = _packed_from_golden(g, m["K"])
+    x1 = g["x1_nan"].reshape(-1, 90)[mask.flatten()]
+    raw1 = r.mlp1(torch.from_numpy(x1).cuda()).cpu().numpy()
+    ref = g["raw1_pad"].reshape(-1, 4)[mask.flatten()]
+    # emulate bf16 operands with fp32 accumulate on the CPU for a like-for-like bound
+    err = np.abs(raw1 - ref)
+    scale = max(1.0, np.abs(ref).max())
+    s_ours = 1 / (1 + np.exp(-raw1.astype(np.float64)))
+    s_ref = 1 / (1 + np.exp(-ref.astype(np.float64)))
+    p = orc.psnr(s_ours, s_ref)
+    print(f"{case}: max|raw1 err|={err.max():.3e} (scale {scale:.2f}) PSNR(sigmoid)={p:.1f} dB")
+    assert np.isfinite(raw1).all()
+    assert err.max() < 0.05 * scale
+    assert p > 45.0
+    r.close()
+
+
+# ------------------------------------------------------------------------------------ stage 5
+@pytest.mark.parametrize("case", CASES)
+def test_stage5_matches_reference(case):
+    g = load_golden(case)
+    m = g["meta"]
+    K = m["K"]
+    r = _renderer(m["scene_params"])
+    mask, ray, z = _packed_from_golden(g, K)
+    cnt = mask.sum(1).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32)
+    raw1 = g["raw1_pad"].reshape(-1, 4)[mask.flatten()]
+    o2 = orc.stage2_sample(torch.from_numpy(g["raw0"]), m["thr"], K, m["scene_params"]["depth_range"])
+    zp = o2["zp"].numpy()[mask]
+    out = r.stage5(torch.from_numpy(raw1), torch.from_numpy(zp), torch.from_numpy(z), torch.from_numpy(off),
+                   torch.from_numpy(cnt), K)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), g["rgb"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["weights"].cpu().numpy(), g["weights"], rtol=0, atol=1e-6)
+    r.close()
+
+
+def test_stage5_dense_warp_path(bare):
+    """K > 32 uses the warp-per-ray product scan; compare with the oracle composite."""
+    g = torch.Generator().manual_seed(9)
+    n, K = 300, 128
+    cnt = torch.randint(1, K + 1, (n,), generator=g, dtype=torch.int32)
+    off = (torch.cumsum(cnt, 0) - cnt).int()
+    M = int(cnt.sum())
+    raw1 = torch.randn(M, 4, generator=g)
+    zp = torch.rand(M, generator=g) * 0.5
+    z = torch.rand(M, generator=g) * 5
+    out = bare.stage5(raw1, zp, z, off, cnt, K)
+    mapping = (torch.arange(K)[None, :] < cnt[:, None]).flatten()
+    zp_pad = torch.zeros(n * K)
+    zp_pad[mapping] = zp
+    ref = orc.stage5_composite(raw1, z, zp_pad.view(n, K), mapping, n, K)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"].numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out["weights"].cpu().numpy(), ref["weights"].numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out["depth_map"].cpu().numpy(), ref["depth_map"].numpy(), rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("case", CASES)
+def test_render_matches_reference(case):
+    g = load_golden(case)
+    m = g["meta"]
+    sd0, sd1 = case_weights(case)
+    r = _renderer(m["scene_params"], sd0, sd1)
+    out = r.render_rays(g["pose"], g["rot"], torch.from_numpy(g["dirs"]).cuda(), m["thr"], m["K"], want_oracle_weights=True)
+    rgb = out["rgb"].cpu().numpy()
+    ns = out["n_samples"].cpu().numpy()
+    same = (ns == np.round(g["asp"] * m["K"]).astype(np.int32))
+    p = orc.psnr(rgb, g["rgb"])
+    print(f"{case}: rays with identical sample count {same.mean():.4f}; PSNR(ours, reference) = {p:.2f} dB")
+    assert np.isfinite(rgb).all()
+    assert same.mean() >= 0.98
+    np.testing.assert_allclose(out["oracle_weights"].cpu().numpy(), g["raw0"], rtol=0, atol=2e-4 * max(1, np.abs(g["raw0"]).max()))
+    if case.startswith("rand"):
+        # untrained nets: alpha*zp leaves [0,1] and amplifies -> relative check only
+        assert np.abs(rgb - g["rgb"]).max() < 0.05 * max(1.0, np.abs(g["rgb"]).max())
+    else:
+        assert p > 45.0
+    host = r.render_rays_host(g["pose"], g["rot"], g["dirs"], m["thr"], m["K"])
+    np.testing.assert_array_equal(host["rgb"], rgb)          # host-buffer entry == device entry, bitwise
+    np.testing.assert_array_equal(host["n_samples"], ns)
+    r.close()
+
+
+def test_render_dense_config1():
+    """BASELINE config 1: first 1024 rays of the 800x800 grid, dense 128 samples, random init."""
+    g = load_golden("rand_dense_k128")
+    m = g["meta"]
+    sd0, sd1 = case_weights("rand_dense_k128")
+    r = _renderer(m["scene_params"], sd0, sd1)
+    out = r.render_rays(g["pose"], g["rot"], torch.from_numpy(g["dirs"]).cuda(), 0.0, 128, want_oracle_weights=True)
+    rgb = out["rgb"].cpu().numpy()
+    assert (out["n_samples"].cpu().numpy() == 128).all()
+    np.testing.assert_allclose(out["oracle_weights"].cpu().numpy(), g["raw0"], rtol=0, atol=2e-4 * np.abs(g["raw0"]).max())
+    scale = max(1.0, np.abs(g["rgb"]).max())
+    rel = np.abs(rgb - g["rgb"]).max() / scale
+    print(f"dense config 1: max rel err {rel:.3e} (|rgb| scale {scale:.3g})")
+    assert np.isfinite(rgb).all()
+    assert rel < 0.05
+    r.close()
+
+
+def test_full_frame_properties_and_tiling():
+    """800x800 frame through adn_render_camera: deterministic; a row band rendered alone equals the
+    same rows of the full frame bit for bit (the multi-GPU tiling invariant); chunked == unchunked."""
+    scene = orc.SCENE_BARBERSHOP
+    sd0, sd1 = orc.make_weights("shaped", seed=0)
+    r = _renderer(scene, sd0, sd1)
+    pose = torch.tensor(scene["view_cell_center"])
+    rot = torch.eye(3)
+    W = H = 800
+    full = r.render_camera(pose, rot, W, H, 0.2, 8, want_nsamples=True)
+    again = r.render_camera(pose, rot, W, H, 0.2, 8, want_nsamples=True)
+    assert torch.equal(full["rgb"], again["rgb"]) and torch.equal(full["n_samples"], again["n_samples"])
+    band = r.render_camera(pose, rot, W, H, 0.2, 8, row0=200, rows=100, want_nsamples=True)
+    assert torch.equal(band["rgb"], full["rgb"][200 * W:300 * W])
+    assert torch.equal(band["n_samples"], full["n_samples"][200 * W:300 * W])
+    r.set_option("chunk_rays", 65536)
+    chunked = r.render_camera(pose, rot, W, H, 0.2, 8)
+    assert torch.equal(chunked["rgb"], full["rgb"])
+    r.set_option("chunk_rays", 0)
+    st = r.stats()
+    assert st["n_samples"] > 0
+    # parity on a strided subset of the frame against the oracle
+    idx = torch.arange(0, W * H, 4099)
+    dirs = torch.from_numpy(orc.generate_ray_directions(W, H, scene["fov"]).reshape(-1, 3)).float()[idx]
+    ref = orc.render_rays(pose, rot, dirs, sd0, sd1, scene, 0.2, 8)
+    p = orc.psnr(full["rgb"].cpu()[idx], ref["rgb"])
+    same = (full["n_samples"].cpu()[idx].long() == ref["n_samples"]).float().mean().item()
+    print(f"full frame subset: PSNR {p:.2f} dB, identical counts {same:.4f}, mean spr {full['n_samples'].float().mean():.2f}")
+    assert p > 45.0 and same > 0.98
+    rgba = r.render_camera_rgba8(pose, rot, W, H, 0.2, 8, row0=0, rows=4).cpu()
+    expect = (full["rgb"][:4 * W].clamp(0, 1) * 255.0).to(torch.uint8).cpu()
+    assert torch.equal(rgba[:, :3], expect) and bool((rgba[:, 3] == 255).all())
+    r.close()
+
+
+def test_error_paths(bare):
+    from adanerf_b200 import AdnError
+    r = _renderer(orc.SCENE_BARBERSHOP)
+    with pytest.raises(AdnError) as e:
+        r.render_camera(torch.zeros(3), torch.eye(3), 8, 8, 0.2, 8)
+    assert e.value.status == 4          # weights not set
+    with pytest.raises(AdnError):
+        r.set_weights(1, {"pts_linears.0.weight": torch.zeros(256, 60)})
+    sd0, sd1 = orc.make_weights("rand", seed=0)
+    r.set_weights(0, sd0)
+    r.set_weights(1, sd1)
+    with pytest.raises(AdnError):
+        r.render_camera(torch.zeros(3), torch.eye(3), 8, 8, 0.0, 8)   # dense needs K == 128
+    with pytest.raises(AdnError):
+        r.render_camera(torch.zeros(3), torch.eye(3), 8, 8, 0.2, 0)
+    r.close()
