@@ -811,7 +811,8 @@ adn_status adn_mlp0_forward(adn_ctx* ctx, const float* d_x0, int64_t n_rays, flo
 adn_status adn_stage2_sample(adn_ctx* ctx, const float* d_raw0, int64_t n_rays, float thr, int K, int32_t* d_count,
                              int32_t* d_offset, int32_t* d_cell, int32_t* d_ray, float* d_z, float* d_zp, int64_t* d_total,
                              void* stream) {
-  if (!ctx || !d_raw0 || !d_count || !d_offset || !d_ray || !d_z || !d_zp || !d_total || n_rays < 0 || K < 1 || K > 128 || !(thr > 0.0f))
+  if (!ctx || !d_total || n_rays < 0 || K < 1 || K > 128 || !(thr > 0.0f) ||
+      (n_rays > 0 && (!d_raw0 || !d_count || !d_offset || !d_ray || !d_z || !d_zp)))
     return fail(ctx, ADN_ERR_INVALID, "stage2: bad arguments (adaptive path needs thr > 0)");
   ADN_CUDA(ctx, cudaSetDevice(ctx->device));
   adn_status s = ensure(ctx, ctx->s2scratch, stage2_scratch_bytes(n_rays));

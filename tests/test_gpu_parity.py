@@ -49,7 +49,8 @@ def test_umma_single_layer(bare, n_out, terms):
     ref = (x.double() @ W.double().T + b.double()).float()
     err = (out - ref).abs().max().item()
     print(f"single layer n_out={n_out} terms={terms}: max abs err {err:.3e}")
-    assert err < (2e-5 if terms == 3 else 6e-2)
+    # bf16x3 keeps ~16 mantissa bits per operand: |err| ~ 2^-16 * |x||w| * sqrt(K)
+    assert err < (2e-4 if terms == 3 else 6e-2)
     bare.set_option("mlp0_terms", 3)
 
 
