@@ -30,7 +30,6 @@ struct Net {
   MlpProgram prog{};
   InputLayout lay{};
   uint8_t* d_wblob = nullptr;
-  float* d_fblob = nullptr;
   std::map<std::string, HostTensor> tensors;  // kept so "mlp0_terms" can re-pack
 };
 
@@ -162,14 +161,13 @@ const HostTensor* find(const Net& n, const std::string& name) {
 }
 
 adn_status upload(adn_ctx* ctx, Net& net, const std::vector<uint8_t>& wblob, const std::vector<float>& fblob) {
+  if (fblob.size() > size_t(kSideFloats)) return fail(ctx, ADN_ERR_INVALID, "network has too many fp32 side parameters");
+  std::memset(net.prog.side, 0, sizeof(net.prog.side));
+  std::memcpy(net.prog.side, fblob.data(), fblob.size() * 4);
   if (net.d_wblob) cudaFree(net.d_wblob);
-  if (net.d_fblob) cudaFree(net.d_fblob);
   net.d_wblob = nullptr;
-  net.d_fblob = nullptr;
   ADN_CUDA(ctx, cudaMalloc(&net.d_wblob, wblob.size()));
-  ADN_CUDA(ctx, cudaMalloc(&net.d_fblob, fblob.size() * 4));
   ADN_CUDA(ctx, cudaMemcpy(net.d_wblob, wblob.data(), wblob.size(), cudaMemcpyHostToDevice));
-  ADN_CUDA(ctx, cudaMemcpy(net.d_fblob, fblob.data(), fblob.size() * 4, cudaMemcpyHostToDevice));
   return ADN_OK;
 }
 
@@ -414,7 +412,7 @@ int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
 adn_status run_mlp(adn_ctx* ctx, int id, const uint8_t* tiles, float* out, const long long* rows_dev, long long rows,
                    cudaStream_t st) {
   Net& n = ctx->net[id];
-  cudaError_t e = launch_mlp(n.nsplit, n.ng, n.prog, n.d_wblob, n.d_fblob, tiles, out, rows_dev, rows, ctx->d_err, ctx->num_sms, st);
+  cudaError_t e = launch_mlp(n.nsplit, n.ng, n.prog, n.d_wblob, tiles, out, rows_dev, rows, ctx->d_err, ctx->num_sms, st);
   if (e != cudaSuccess) return cuda_fail(ctx, e, id == 0 ? "launch sampling MLP" : "launch shading MLP");
   ctx->stats.kernel_launches++;
   return ADN_OK;
@@ -613,7 +611,6 @@ void adn_destroy(adn_ctx* ctx) {
     if (b->p) cudaFreeHost(b->p);
   for (int i = 0; i < 2; ++i) {
     if (ctx->net[i].d_wblob) cudaFree(ctx->net[i].d_wblob);
-    if (ctx->net[i].d_fblob) cudaFree(ctx->net[i].d_fblob);
   }
   if (ctx->d_zlut) cudaFree(ctx->d_zlut);
   if (ctx->d_zlut_dense) cudaFree(ctx->d_zlut_dense);
@@ -728,7 +725,7 @@ adn_status adn_render_rays_host(adn_ctx* ctx, const float* pose, const float* ro
   cudaStream_t st = ctx->own_stream;
   std::memcpy(ctx->h_in.p, h_dirs, size_t(n_rays) * 12);
   ADN_CUDA(ctx, cudaMemcpyAsync(ctx->dirs.p, ctx->h_in.p, size_t(n_rays) * 12, cudaMemcpyHostToDevice, st));
-  Buf ns{};  // separate nsamples buffer so render_chunk's count scratch is not aliased across chunks
+
   int32_t* d_ns = nullptr;
   if (h_nsamples) {
     if ((s = ensure(ctx, ctx->rgba, size_t(n_rays) * 4)) != ADN_OK) return s;
@@ -742,7 +739,7 @@ adn_status adn_render_rays_host(adn_ctx* ctx, const float* pose, const float* ro
   ADN_CUDA(ctx, cudaStreamSynchronize(st));
   std::memcpy(h_rgb, ctx->h_out.p, size_t(n_rays) * 12);
   if (h_nsamples) std::memcpy(h_nsamples, ctx->h_ns.p, size_t(n_rays) * 4);
-  (void)ns;
+
   return check_device_error(ctx);
 }
 

@@ -29,39 +29,57 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// ReLU folded into the fp32 -> bf16x2 conversion (one instruction for two elements); a -> low half.
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 
-// Epilogue for 32 consecutive accumulator columns [c, c+32) of one row.
-template <int NSPLIT>
+// Epilogue kinds (derived from the layer flags once per layer, so the per-element code is branch free).
+enum : int { EK_ACT_RELU = 0, EK_ACT_RELU_ALPHA = 1, EK_ACT_LINEAR = 2, EK_FINAL_RGB = 3, EK_FINAL_RAW = 4 };
+
+__device__ __forceinline__ int epilogue_kind(uint8_t flags) {
+  if (flags & LF_FINAL_RAW) return EK_FINAL_RAW;
+  if (flags & LF_FINAL_RGB) return EK_FINAL_RGB;
+  if (!(flags & LF_RELU)) return EK_ACT_LINEAR;
+  return (flags & LF_ALPHA_DOT) ? EK_ACT_RELU_ALPHA : EK_ACT_RELU;
+}
+
+// Epilogue for 32 consecutive accumulator columns [c, c+32) of one row (thread = row).
+template <int NSPLIT, int KIND>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, const MlpLayer& L, const MlpProgram& prog,
-                                               const float* __restrict__ fblob, uint8_t* act_hi, uint8_t* act_lo,
-                                               int row_in_tile, long long grow, long long rows, float* __restrict__ out,
-                                               float& alpha, float (&rgb)[3]) {
+                                               uint32_t act_hi, uint32_t act_lo, int row_in_tile, long long grow,
+                                               long long rows, float* __restrict__ out, float& alpha, float (&rgb)[3]) {
+  constexpr bool kRelu = (KIND == EK_ACT_RELU || KIND == EK_ACT_RELU_ALPHA || KIND == EK_FINAL_RGB);
+  constexpr bool kAct = (KIND == EK_ACT_RELU || KIND == EK_ACT_RELU_ALPHA || KIND == EK_ACT_LINEAR);
   float v[32];
-  const float4* b4 = reinterpret_cast<const float4*>(fblob + L.bias_off + c);
+  const float4* bias = reinterpret_cast<const float4*>(prog.side) + ((L.bias_off + c) >> 2);   // warp-uniform, constant bank
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(b4 + j);
+    const float4 b = bias[j];
     v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
     v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
     v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
     v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
   }
-  if (L.flags & LF_RELU) {
+  constexpr bool kFusedReluPack = (NSPLIT == 1 && KIND == EK_ACT_RELU);   // relu inside the bf16 pack
+  if (kRelu && !kFusedReluPack) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
-  if (L.flags & LF_ALPHA_DOT) {
-    const float4* w4 = reinterpret_cast<const float4*>(fblob + prog.alpha_w_off + c);
+  if (KIND == EK_ACT_RELU_ALPHA) {
+    const float4* w4 = reinterpret_cast<const float4*>(prog.side) + ((prog.alpha_w_off + c) >> 2);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 w = __ldg(w4 + j);
+      const float4 w = w4[j];
       alpha = fmaf(v[4 * j + 0], w.x, alpha);
       alpha = fmaf(v[4 * j + 1], w.y, alpha);
       alpha = fmaf(v[4 * j + 2], w.z, alpha);
       alpha = fmaf(v[4 * j + 3], w.w, alpha);
     }
   }
-  if (L.flags & LF_OUT_ACT) {
+  if (kAct) {
     // columns [c, c+32) -> block out_blk0 + c/64, 16-byte chunks (c%64)/8 .. +3, XOR-swizzled by row%8
     const uint32_t blk = L.out_blk0 + (c >> 6);
     const uint32_t rbase = blk * kBlkBytes + (row_in_tile >> 3) * 1024u + (row_in_tile & 7) * 128u;
@@ -69,12 +87,19 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, c
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 hi;
-      hi.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-      hi.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-      hi.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-      hi.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      if (kFusedReluPack) {
+        hi.x = pack_relu_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+        hi.y = pack_relu_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+        hi.z = pack_relu_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+        hi.w = pack_relu_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      } else {
+        hi.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+        hi.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+        hi.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+        hi.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      }
       const uint32_t off = rbase + (((cc0 + q) ^ (row_in_tile & 7)) << 4);
-      *reinterpret_cast<uint4*>(act_hi + off) = hi;
+      st_shared_v4(act_hi + off, hi.x, hi.y, hi.z, hi.w);
       if (NSPLIT == 2) {
         float l[8];
         const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
@@ -88,25 +113,25 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, c
         lo.y = pack_bf16x2(l[2], l[3]);
         lo.z = pack_bf16x2(l[4], l[5]);
         lo.w = pack_bf16x2(l[6], l[7]);
-        *reinterpret_cast<uint4*>(act_lo + off) = lo;
+        st_shared_v4(act_lo + off, lo.x, lo.y, lo.z, lo.w);
       }
     }
   }
-  if (L.flags & LF_FINAL_RAW) {
+  if (KIND == EK_FINAL_RAW) {
     if (grow < rows) {
       float4* o4 = reinterpret_cast<float4*>(out + grow * prog.out_cols + c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   }
-  if (L.flags & LF_FINAL_RGB) {
+  if (KIND == EK_FINAL_RGB) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float4* w4 = reinterpret_cast<const float4*>(fblob + prog.rgb_w_off + k * 128 + c);
+      const float4* w4 = reinterpret_cast<const float4*>(prog.side) + ((prog.rgb_w_off + k * 128 + c) >> 2);
       float acc = rgb[k];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 w = __ldg(w4 + j);
+        const float4 w = w4[j];
         acc = fmaf(v[4 * j + 0], w.x, acc);
         acc = fmaf(v[4 * j + 1], w.y, acc);
         acc = fmaf(v[4 * j + 2], w.z, acc);
@@ -117,10 +142,25 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, c
   }
 }
 
+// All accumulator columns [c0, c0 + span) of one layer for this thread's row.
+template <int NSPLIT, int KIND>
+__device__ __forceinline__ void epilogue_layer(uint32_t taddr, int c0, int span, const MlpLayer& L, const MlpProgram& prog,
+                                               uint32_t act_hi, uint32_t act_lo, int row_in_tile, long long grow,
+                                               long long rows, float* __restrict__ out, float& alpha, float (&rgb)[3]) {
+  for (int c = c0; c < c0 + span; c += 64) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32(taddr + c, ra);
+    tmem_ld32(taddr + c + 32, rb);
+    tc_wait_ld();
+    epilogue_chunk<NSPLIT, KIND>(ra, c, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+    epilogue_chunk<NSPLIT, KIND>(rb, c + 32, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+  }
+}
+
 template <int NSPLIT, int NG>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict__ wblob,
-                const float* __restrict__ fblob, const uint8_t* __restrict__ in_tiles, float* __restrict__ out,
+                const uint8_t* __restrict__ in_tiles, float* __restrict__ out,
                 const long long* __restrict__ rows_dev, long long rows_host, int* err_flag) {
   using Cfg = MlpCfg<NSPLIT>;
   constexpr int NB = Cfg::kNB;
@@ -140,7 +180,9 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   uint64_t* in_full = act_ready + NG;      // [NG]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + NG);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a lane-0 broadcast: tells the compiler it is warp uniform, so the role branches
+  // (and everything indexed by loop counters inside them) stay on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   const long long rows = rows_dev ? *rows_dev : rows_host;
@@ -202,52 +244,65 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     }
   } else if (warp == 1) {
     // ========================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t in_phase[NG], ar_phase[NG];
-      for (int g = 0; g < NG; ++g) in_phase[g] = ar_phase[g] = 0;
-      for (long long iter = 0;; ++iter) {
-        if (tile_of(iter, 0) >= n_tiles) break;
-        for (int l = 0; l < prog.n_layers; ++l) {
-          const MlpLayer& L = prog.layers[l];
-          for (int g = 0; g < NG; ++g) {
-            if (tile_of(iter, g) >= n_tiles) continue;
-            if (l == 0 || (L.flags & LF_WAIT_IN)) {
-              mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
-              in_phase[g] ^= 1;
-            }
-            mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
-            ar_phase[g] ^= 1;
-            tc_fence_after();
-            for (int kb = 0; kb < L.n_kb; ++kb) {
-              const uint32_t a_hi = smem_u32(act_ptr(g, 0, L.a_blk[kb]));
-              const uint32_t a_lo = (NSPLIT == 2) ? smem_u32(act_ptr(g, NSPLIT - 1, L.a_blk[kb])) : 0u;
-              for (int nh = 0; nh < L.n_half; ++nh) {
-                mbar_wait(&w_full[stage], phase, err_flag, 4);
-                tc_fence_after();
-                const uint32_t b_hi = smem_u32(ring + size_t(stage) * STAGE_BYTES);
-                const uint32_t b_lo = b_hi + kBlkBytes;
-                const uint32_t d = tmem_base + uint32_t(g * 256 + nh * 128);
+    // The whole warp walks the schedule converged (every quantity below is warp uniform, so the
+    // descriptors live in uniform registers); one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t in_phase[NG], ar_phase[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) in_phase[g] = ar_phase[g] = 0;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint64_t desc_hi = make_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // constant upper half
+    const uint32_t desc_lo_const = uint32_t(make_desc_sw128(0) & 0xFFFF0000ull);
+    auto desc_of = [&](uint32_t addr) -> uint64_t {
+      return desc_hi | uint64_t(desc_lo_const | ((addr & 0x3FFFFu) >> 4));
+    };
+    for (long long iter = 0;; ++iter) {
+      if (tile_of(iter, 0) >= n_tiles) break;
+      for (int l = 0; l < prog.n_layers; ++l) {
+        const MlpLayer& L = prog.layers[l];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (tile_of(iter, g) >= n_tiles) continue;
+          if (l == 0 || (L.flags & LF_WAIT_IN)) {
+            mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
+            in_phase[g] ^= 1;
+          }
+          mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
+          ar_phase[g] ^= 1;
+          tc_fence_after();
+          const uint32_t act_g = smem_u32(act) + uint32_t(g * NSPLIT * NB) * kBlkBytes;
+          for (int kb = 0; kb < L.n_kb; ++kb) {
+            const uint32_t a_hi = act_g + uint32_t(L.a_blk[kb]) * kBlkBytes;
+            const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * kBlkBytes;
+            for (int nh = 0; nh < L.n_half; ++nh) {
+              mbar_wait(&w_full[stage], phase, err_flag, 4);
+              tc_fence_after();
+              const uint32_t b_hi = ring_u32 + uint32_t(stage) * STAGE_BYTES;
+              const uint32_t b_lo = b_hi + kBlkBytes;
+              const uint32_t d = tmem_base + uint32_t(g * 256 + nh * 128);
+              if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                  umma_bf16(d, make_desc_sw128(a_hi + k * 32), make_desc_sw128(b_hi + k * 32), idesc, acc);
+                  umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_hi + k * 32), idesc, acc);
                   if (NSPLIT == 2) {
-                    umma_bf16(d, make_desc_sw128(a_lo + k * 32), make_desc_sw128(b_hi + k * 32), idesc, 1u);
-                    umma_bf16(d, make_desc_sw128(a_hi + k * 32), make_desc_sw128(b_lo + k * 32), idesc, 1u);
+                    umma_bf16(d, desc_of(a_lo + k * 32), desc_of(b_hi + k * 32), idesc, 1u);
+                    umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_lo + k * 32), idesc, 1u);
                   }
                 }
                 umma_commit(&w_empty[stage]);
-                if (++stage == STAGES) {
-                  stage = 0;
-                  phase ^= 1;
-                }
+              }
+              __syncwarp();
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
               }
             }
-            umma_commit(&acc_full[g]);
           }
+          if (elect_one()) umma_commit(&acc_full[g]);
+          __syncwarp();
         }
       }
     }
@@ -260,8 +315,8 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     const int col_half = (NG == 2) ? 0 : (ew >> 2);
     const int row_in_tile = quarter * 32 + lane;
     uint32_t acc_phase = 0;
-    uint8_t* act_hi = act_ptr(g, 0, 0);
-    uint8_t* act_lo = act_ptr(g, NSPLIT - 1, 0);
+    const uint32_t act_hi = smem_u32(act_ptr(g, 0, 0));
+    const uint32_t act_lo = smem_u32(act_ptr(g, NSPLIT - 1, 0));
     for (long long iter = 0;; ++iter) {
       const long long t = tile_of(iter, g);
       if (t >= n_tiles) break;
@@ -294,19 +349,27 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         const int span = (NG == 2) ? n_cols : (n_cols >> 1);
         const int c0 = col_half * span;
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(g * 256);
-        for (int c = c0; c < c0 + span; c += 64) {
-          uint32_t ra[32], rb[32];
-          tmem_ld32(taddr + c, ra);
-          tmem_ld32(taddr + c + 32, rb);
-          tc_wait_ld();
-          epilogue_chunk<NSPLIT>(ra, c, L, prog, fblob, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-          epilogue_chunk<NSPLIT>(rb, c + 32, L, prog, fblob, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+        switch (epilogue_kind(L.flags)) {
+          case EK_ACT_RELU:
+            epilogue_layer<NSPLIT, EK_ACT_RELU>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+            break;
+          case EK_ACT_RELU_ALPHA:
+            epilogue_layer<NSPLIT, EK_ACT_RELU_ALPHA>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+            break;
+          case EK_ACT_LINEAR:
+            epilogue_layer<NSPLIT, EK_ACT_LINEAR>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+            break;
+          case EK_FINAL_RGB:
+            epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+            break;
+          default:
+            epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+            break;
         }
         if (L.flags & LF_FINAL_RGB) {
           if (grow < rows) {
-            const float ab = __ldg(fblob + prog.alpha_b_off);
-            const float b0 = __ldg(fblob + prog.rgb_b_off), b1 = __ldg(fblob + prog.rgb_b_off + 1),
-                        b2 = __ldg(fblob + prog.rgb_b_off + 2);
+            const float ab = prog.side[prog.alpha_b_off];
+            const float b0 = prog.side[prog.rgb_b_off], b1 = prog.side[prog.rgb_b_off + 1], b2 = prog.side[prog.rgb_b_off + 2];
             reinterpret_cast<float4*>(out)[grow] = make_float4(rgb[0] + b0, rgb[1] + b1, rgb[2] + b2, alpha + ab);
           }
         }
@@ -377,7 +440,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, long long rows_hos
 
 // -------------------------------------------------------------------------------------------------
 template <int NSPLIT, int NG>
-static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, const float* fblob, const uint8_t* in_tiles,
+static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles,
                                 float* out, const long long* rows_dev, long long rows_host, int* err_flag, int num_sms,
                                 cudaStream_t stream) {
   static bool attr_set = false;
@@ -393,17 +456,17 @@ static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, co
     const long long need = (n_tiles + NG - 1) / NG;
     if (need < grid) grid = int(need < 1 ? 1 : need);
   }
-  mlp_umma_kernel<NSPLIT, NG><<<grid, kMlpThreads, smem, stream>>>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host,
+  mlp_umma_kernel<NSPLIT, NG><<<grid, kMlpThreads, smem, stream>>>(prog, wblob, in_tiles, out, rows_dev, rows_host,
                                                                    err_flag);
   return cudaGetLastError();
 }
 
-cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob, const float* fblob,
+cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host, int* err_flag,
                        int num_sms, cudaStream_t stream) {
-  if (nsplit == 2) return launch_mlp_t<2, 1>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
-  if (ng == 2) return launch_mlp_t<1, 2>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
-  return launch_mlp_t<1, 1>(prog, wblob, fblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
+  if (nsplit == 2) return launch_mlp_t<2, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
+  if (ng == 2) return launch_mlp_t<1, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
+  return launch_mlp_t<1, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
 }
 
 cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat, const InputLayout& lay,

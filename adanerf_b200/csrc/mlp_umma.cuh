@@ -21,6 +21,7 @@ constexpr int kTileM = 128;
 constexpr int kBlkBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B block
 constexpr int kMaxLayers = 12;
 constexpr int kMlpThreads = 320;  // 10 warps
+constexpr int kSideFloats = 3200; // fp32 side parameters (biases, alpha / rgb heads) carried in the kernel parameters
 
 enum : uint8_t {
   LF_RELU = 1,
@@ -34,7 +35,7 @@ enum : uint8_t {
 
 struct MlpLayer {
   uint32_t w_off;     // byte offset of this layer's packed weight stages (consumption order)
-  uint32_t bias_off;  // float offset of the bias vector in the fp32 side blob
+  uint32_t bias_off;  // float offset of the bias vector in MlpProgram::side
   uint8_t n_kb;       // number of 64-wide K blocks
   uint8_t a_blk[5];   // activation block index per K block
   uint8_t n_half;     // N / 128  (1 or 2)
@@ -49,9 +50,12 @@ struct MlpProgram {
   int32_t in1_blk;            // 2nd input destination block
   uint32_t in_tile_stride;    // bytes per tile in the packed input buffer
   uint32_t in0_off, in0_lo_off, in1_off;
-  uint32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;  // float offsets in the side blob
+  uint32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;  // float offsets in `side`
   int32_t out_cols;           // row stride of the FINAL_RAW output
   MlpLayer layers[kMaxLayers];
+  // Biases and the two tiny heads live in the kernel parameter (constant) bank: every lane of a warp reads
+  // the same column's value, so the epilogue gets them through uniform constant loads, not the LSU.
+  float side[kSideFloats];
 };
 
 // Describes how fp32 feature rows map onto the packed bf16 input blocks of a tile.
@@ -68,7 +72,7 @@ struct InputLayout {
 size_t mlp_smem_bytes(int nsplit, int ng);
 
 // Launchers (defined in mlp_umma.cu).  rows_dev may be null (then rows_host is used).
-cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob, const float* fblob,
+cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host,
                        int* err_flag, int num_sms, cudaStream_t stream);
 cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat,

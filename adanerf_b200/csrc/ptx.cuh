@@ -10,6 +10,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp (elect.sync): keeps the surrounding code warp-uniform for the compiler.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -27,12 +38,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the hardware park the thread instead of spinning through the issue slots
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -42,8 +54,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef ADN_WATCHDOG_CYCLES
 #define ADN_WATCHDOG_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int site) {
-  if (mbar_try_wait(bar, parity)) return;
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* err_flag, int site) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > ADN_WATCHDOG_CYCLES) {
@@ -52,6 +63,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
       asm volatile("trap;");
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int site) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, err_flag, site);
 }
 
 // --------------------------------------------------------------------------- async bulk copy

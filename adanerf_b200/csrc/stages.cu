@@ -184,25 +184,24 @@ cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_
 constexpr int kS2Rays = 64;     // rays per CTA
 constexpr int kS2Threads = 256;  // 8 warps x 8 rays
 
-struct ValIdx {
-  float v;
-  int i;
-};
-__device__ __forceinline__ bool better(const ValIdx& a, const ValIdx& b) {  // a precedes b in sort order
-  return (a.v > b.v) || (a.v == b.v && a.i < b.i);
+// Order-preserving map float -> uint32 (larger float <-> larger key); -0.0 is folded onto +0.0 so it ties
+// with it like a float compare does.  Every real input maps to a key >= 0x007FFFFF, so 0 means "no entry".
+__device__ __forceinline__ uint32_t order_key(float v) {
+  const uint32_t u = __float_as_uint(v + 0.0f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__device__ __forceinline__ ValIdx warp_best(ValIdx x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ValIdx y;
-    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
-    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
-    if (better(y, x)) x = y;
-  }
-  return x;
+
+__device__ __forceinline__ void cswap_desc(unsigned long long& a, unsigned long long& b) {
+  const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+  a = hi;
+  b = lo;
 }
 
 // Returns the 4 selection masks (bit l of sel[j] <-> cell 4l+j) and the count, warp uniform.
+// More than K survivors: K rounds of "pop the best head".  Each lane keeps its (up to 4) candidates as
+// 64-bit composites (order_key << 2 | 3 - j), sorted descending, so the head of every lane is its best
+// remaining cell; one REDUX.MAX over the heads + a ballot finds the winner (ties: lowest lane = lowest
+// cell, and inside a lane the lower j sorts first), and only the winning lane pops.
 __device__ __forceinline__ int select_cells(const float4 v4, float thr, int K, int lane, uint32_t (&sel)[4]) {
   const float v[4] = {v4.x, v4.y, v4.z, v4.w};
   uint32_t act[4];
@@ -212,46 +211,40 @@ __device__ __forceinline__ int select_cells(const float4 v4, float thr, int K, i
     act[j] = __ballot_sync(0xffffffffu, v[j] >= thr);
     cnt += __popc(act[j]);
   }
-  if (cnt == 0) {
-    ValIdx b{-INFINITY, 1 << 20};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      ValIdx c{v[j], 4 * lane + j};
-      if (better(c, b)) b = c;
-    }
-    b = warp_best(b);
-    const int cell = (b.i < 128) ? b.i : 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) sel[j] = ((cell & 3) == j) ? (1u << (cell >> 2)) : 0u;
-    return 1;
-  }
-  if (cnt <= K) {
+  if (cnt > 0 && cnt <= K) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) sel[j] = act[j];
     return cnt;
   }
-  uint32_t mine = 0;  // bit j: my cell j is still a candidate
+  const bool fallback = (cnt == 0);          // nothing >= thr: the arg-max cell (:748-749)
+  const int need = fallback ? 1 : K;
+  unsigned long long h[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) mine |= ((act[j] >> lane) & 1u) << j;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) sel[j] = 0;
-  for (int round = 0; round < K; ++round) {
-    ValIdx b{-INFINITY, 1 << 20};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if ((mine >> j) & 1u) {
-        ValIdx c{v[j], 4 * lane + j};
-        if (better(c, b)) b = c;
-      }
-    }
-    b = warp_best(b);
-    const int cell = b.i;
-    if ((cell >> 2) == lane) mine &= ~(1u << (cell & 3));
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if ((cell & 3) == j) sel[j] |= 1u << (cell >> 2);
+  for (int j = 0; j < 4; ++j) {
+    const bool cand = fallback || ((act[j] >> lane) & 1u);
+    h[j] = cand ? (((unsigned long long)order_key(v[j]) << 2) | (unsigned long long)(3 - j)) : 0ull;
   }
-  return K;
+  cswap_desc(h[0], h[1]);
+  cswap_desc(h[2], h[3]);
+  cswap_desc(h[0], h[2]);
+  cswap_desc(h[1], h[3]);
+  cswap_desc(h[1], h[2]);
+  uint32_t mine = 0;
+  for (int round = 0; round < need; ++round) {
+    const uint32_t head = uint32_t(h[0] >> 2);
+    const uint32_t m = __reduce_max_sync(0xffffffffu, head);
+    const uint32_t who = __ballot_sync(0xffffffffu, head == m);
+    if (lane == __ffs(who) - 1) {
+      mine |= 1u << (3 - int(h[0] & 3ull));
+      h[0] = h[1];
+      h[1] = h[2];
+      h[2] = h[3];
+      h[3] = 0ull;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sel[j] = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
+  return need;
 }
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -271,7 +264,6 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
   __shared__ int s_off[kS2Rays];
   __shared__ long long s_prefix;
   __shared__ int s_tile;
-  __shared__ int s_tile_total;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) s_tile = int(atomicAdd(ticket, 1u));
@@ -279,17 +271,20 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
   const int tile = s_tile;
   const long long ray0 = (long long)tile * kS2Rays;
 
-  // phase 1: selection
-#pragma unroll 1
+  // phase 1: selection (the warp's 8 row loads are issued up front: 8 x 512 B in flight per warp)
+  float4 rows8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long r = ray0 + warp * 8 + i;
+    rows8[i] = (r < n_rays) ? __ldg(reinterpret_cast<const float4*>(raw0 + r * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rl = warp * 8 + i;
     const long long r = ray0 + rl;
     int cnt = 0;
     uint32_t sel[4] = {0, 0, 0, 0};
-    if (r < n_rays) {
-      const float4 v4 = __ldg(reinterpret_cast<const float4*>(raw0 + r * 128) + lane);
-      cnt = select_cells(v4, thr, K, lane, sel);
-    }
+    if (r < n_rays) cnt = select_cells(rows8[i], thr, K, lane, sel);
     if (lane == 0) {
       s_cnt[rl] = cnt;
 #pragma unroll
@@ -346,7 +341,6 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
       __threadfence();
       atomicExch(&tile_state[tile], FLAG_INC | (unsigned long long)(prefix + tile_total));
       s_prefix = prefix;
-      s_tile_total = tile_total;
       if (tile == n_tiles - 1) *total = prefix + tile_total;
     }
   }
@@ -354,12 +348,12 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
   const long long prefix = s_prefix;
 
   // phase 2: write the packed samples (ray-major, ascending cell)
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rl = warp * 8 + i;
     const long long r = ray0 + rl;
     if (r >= n_rays) break;
-    const float4 v4 = __ldg(reinterpret_cast<const float4*>(raw0 + r * 128) + lane);
+    const float4 v4 = rows8[i];
     const float v[4] = {v4.x, v4.y, v4.z, v4.w};
     const long long off = prefix + s_off[rl];
     if (lane == 0) {
