@@ -121,12 +121,12 @@ struct Seg {
   int col0, valid;
 };
 
-// Packs one layer's weights W [n_out, k_in] into the ring-stage stream: for each K block (Seg), for each
-// 128-row N half: a [128 x 64] K-major SWIZZLE_128B bf16 tile (hi), followed by the lo tile when nsplit == 2.
+// Packs one layer's weights W [n_out, k_in] into the ring-stage stream: for each 128-row N half, for each
+// K block (Seg): a [128 x 64] K-major SWIZZLE_128B bf16 tile (hi), followed by the lo tile when nsplit == 2.
 void pack_layer(const float* W, int n_out, int k_in, const std::vector<Seg>& segs, int nsplit, std::vector<uint8_t>& blob) {
   const int n_half = (n_out + 127) / 128;
-  for (const Seg& sg : segs) {
-    for (int nh = 0; nh < n_half; ++nh) {
+  for (int nh = 0; nh < n_half; ++nh) {       // N half outermost: half 0's accumulator completes first
+    for (const Seg& sg : segs) {
       const size_t base = blob.size();
       blob.resize(base + size_t(nsplit) * kBlkBytes, 0);
       for (int n = 0; n < 128; ++n) {
@@ -223,6 +223,7 @@ adn_status build_net0(adn_ctx* ctx) {
   P.in0_blk = 0;
   P.in0_nblk = 2;
   P.in1_blk = 0;
+  P.hid_blk0 = 0;
   P.in_tile_stride = uint32_t(2 * nsplit * kBlkBytes);
   P.in0_off = 0;
   P.in0_lo_off = 2 * kBlkBytes;
@@ -337,6 +338,7 @@ adn_status build_net1(adn_ctx* ctx) {
   P.in0_blk = 0;
   P.in0_nblk = 1;
   P.in1_blk = 0;
+  P.hid_blk0 = 1;
   P.in_tile_stride = 2 * kBlkBytes;
   P.in0_off = 0;
   P.in0_lo_off = 0;

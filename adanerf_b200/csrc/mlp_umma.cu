@@ -147,13 +147,12 @@ template <int NSPLIT, int KIND>
 __device__ __forceinline__ void epilogue_layer(uint32_t taddr, int c0, int span, const MlpLayer& L, const MlpProgram& prog,
                                                uint32_t act_hi, uint32_t act_lo, int row_in_tile, long long grow,
                                                long long rows, float* __restrict__ out, float& alpha, float (&rgb)[3]) {
-  for (int c = c0; c < c0 + span; c += 64) {
-    uint32_t ra[32], rb[32];
+#pragma unroll 1
+  for (int c = c0; c < c0 + span; c += 32) {
+    uint32_t ra[32];
     tmem_ld32(taddr + c, ra);
-    tmem_ld32(taddr + c + 32, rb);
     tc_wait_ld();
     epilogue_chunk<NSPLIT, KIND>(ra, c, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-    epilogue_chunk<NSPLIT, KIND>(rb, c + 32, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
   }
 }
 
@@ -166,18 +165,20 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   constexpr int NB = Cfg::kNB;
   constexpr int STAGES = Cfg::kStages;
   constexpr int STAGE_BYTES = Cfg::kStageBytes;
-  constexpr int EW = 8 / NG;  // epilogue warps per tile slot
+  constexpr int EW = 16 / NG;  // epilogue warps per tile slot
+  constexpr int QW = EW / 4;    // warps sharing one TMEM lane quarter (they split the columns)
+  constexpr int CW = 128 / QW;  // accumulator columns per warp and N half
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* act = smem;                                                   // [NG][NSPLIT][NB] blocks
   uint8_t* ring = act + size_t(NG) * NSPLIT * NB * kBlkBytes;            // [STAGES] stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(STAGES) * STAGE_BYTES);
-  uint64_t* w_full = bars;                 // [STAGES]
-  uint64_t* w_empty = bars + STAGES;       // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;  // [NG]
-  uint64_t* act_ready = acc_full + NG;     // [NG]
-  uint64_t* in_full = act_ready + NG;      // [NG]
+  uint64_t* w_full = bars;                     // [STAGES]
+  uint64_t* w_empty = bars + STAGES;           // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;      // [NG][2]  accumulator half (128 columns) complete
+  uint64_t* act_ready = acc_full + 2 * NG;     // [NG][2]  epilogue of that half done (TMEM half free, A blocks written)
+  uint64_t* in_full = act_ready + 2 * NG;      // [NG]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + NG);
 
   // warp index through a lane-0 broadcast: tells the compiler it is warp uniform, so the role branches
@@ -194,8 +195,10 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       mbar_init(&w_empty[s], 1);
     }
     for (int g = 0; g < NG; ++g) {
-      mbar_init(&acc_full[g], 1);
-      mbar_init(&act_ready[g], EW);
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(&acc_full[2 * g + h], 1);
+        mbar_init(&act_ready[2 * g + h], EW);
+      }
       mbar_init(&in_full[g], 1);
     }
     mbar_fence_init();
@@ -265,54 +268,70 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           if (tile_of(iter, g) >= n_tiles) continue;
-          if (l == 0 || (L.flags & LF_WAIT_IN)) {
-            mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
-            in_phase[g] ^= 1;
-          }
-          mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
-          ar_phase[g] ^= 1;
-          tc_fence_after();
-          const uint32_t act_g = smem_u32(act) + uint32_t(g * NSPLIT * NB) * kBlkBytes;
-          for (int kb = 0; kb < L.n_kb; ++kb) {
-            const uint32_t a_hi = act_g + uint32_t(L.a_blk[kb]) * kBlkBytes;
-            const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * kBlkBytes;
-            for (int nh = 0; nh < L.n_half; ++nh) {
-              mbar_wait(&w_full[stage], phase, err_flag, 4);
+          // Per layer exactly one phase of act_ready[g][0..1] is consumed: half h of the previous layer's
+          // epilogue frees TMEM columns [128h, 128h+128) and publishes hidden blocks hid_blk0 + 2h, +1.
+          bool waited[2] = {false, false};
+          bool in_waited = false;
+          auto ensure = [&](int h) {
+            if (!waited[h]) {
+              mbar_wait(&act_ready[2 * g + h], ar_phase[g], err_flag, 3);
               tc_fence_after();
-              const uint32_t b_hi = ring_u32 + uint32_t(stage) * STAGE_BYTES;
-              const uint32_t b_lo = b_hi + kBlkBytes;
-              const uint32_t d = tmem_base + uint32_t(g * 256 + nh * 128);
-              if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                  umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_hi + k * 32), idesc, acc);
-                  if (NSPLIT == 2) {
-                    umma_bf16(d, desc_of(a_lo + k * 32), desc_of(b_hi + k * 32), idesc, 1u);
-                    umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_lo + k * 32), idesc, 1u);
-                  }
+              waited[h] = true;
+            }
+          };
+          const uint32_t act_g = smem_u32(act) + uint32_t(g * NSPLIT * NB) * kBlkBytes;
+          for (int nh = 0; nh < 2; ++nh) {
+            ensure(nh);
+            if (nh < L.n_half) {
+              for (int kb = 0; kb < L.n_kb; ++kb) {
+                const int blk = L.a_blk[kb];
+                if (blk >= prog.hid_blk0 && l > 0) {
+                  ensure((blk - prog.hid_blk0) >> 1);
+                } else if (!in_waited && (l == 0 || (L.flags & LF_WAIT_IN))) {
+                  mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
+                  in_phase[g] ^= 1;
+                  in_waited = true;
                 }
-                umma_commit(&w_empty[stage]);
-              }
-              __syncwarp();
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
+                const uint32_t a_hi = act_g + uint32_t(blk) * kBlkBytes;
+                const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * kBlkBytes;
+                mbar_wait(&w_full[stage], phase, err_flag, 4);
+                tc_fence_after();
+                const uint32_t b_hi = ring_u32 + uint32_t(stage) * STAGE_BYTES;
+                const uint32_t b_lo = b_hi + kBlkBytes;
+                const uint32_t d = tmem_base + uint32_t(g * 256 + nh * 128);
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                    umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_hi + k * 32), idesc, acc);
+                    if (NSPLIT == 2) {
+                      umma_bf16(d, desc_of(a_lo + k * 32), desc_of(b_hi + k * 32), idesc, 1u);
+                      umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_lo + k * 32), idesc, 1u);
+                    }
+                  }
+                  umma_commit(&w_empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
+            if (elect_one()) umma_commit(&acc_full[2 * g + nh]);
+            __syncwarp();
           }
-          if (elect_one()) umma_commit(&acc_full[g]);
-          __syncwarp();
+          ar_phase[g] ^= 1;
         }
       }
     }
   } else {
     // ============================================================================ epilogue
-    const int ew = warp - 2;                       // 0..7
-    const int g = (NG == 2) ? (ew >> 2) : 0;       // tile slot
-    const int e = (NG == 2) ? (ew & 3) : ew;       // index inside the slot's warp set
+    const int ew = warp - 2;                       // 0..15
+    const int g = ew / EW;                         // tile slot
+    const int e = ew % EW;                         // index inside the slot's warp set
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-    const int col_half = (NG == 2) ? 0 : (ew >> 2);
+    const int sub = e >> 2;                        // which column slice of each N half this warp owns
     const int row_in_tile = quarter * 32 + lane;
     uint32_t acc_phase = 0;
     const uint32_t act_hi = smem_u32(act_ptr(g, 0, 0));
@@ -331,53 +350,81 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       // accumulator columns and activation buffers of this slot are free for layer 0
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&act_ready[g]);
+      if (lane == 0) {
+        mbar_arrive(&act_ready[2 * g + 0]);
+        mbar_arrive(&act_ready[2 * g + 1]);
+      }
 
       float alpha = 0.0f;
       float rgb[3] = {0.0f, 0.0f, 0.0f};
       for (int l = 0; l < prog.n_layers; ++l) {
         const MlpLayer& L = prog.layers[l];
-        mbar_wait(&acc_full[g], acc_phase, err_flag, 5);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
-          mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
-          bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
-                   &in_full[g]);
-        }
-        const int n_cols = int(L.n_half) * 128;
-        const int span = (NG == 2) ? n_cols : (n_cols >> 1);
-        const int c0 = col_half * span;
+        const int kind = epilogue_kind(L.flags);
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(g * 256);
-        switch (epilogue_kind(L.flags)) {
-          case EK_ACT_RELU:
-            epilogue_layer<NSPLIT, EK_ACT_RELU>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-            break;
-          case EK_ACT_RELU_ALPHA:
-            epilogue_layer<NSPLIT, EK_ACT_RELU_ALPHA>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-            break;
-          case EK_ACT_LINEAR:
-            epilogue_layer<NSPLIT, EK_ACT_LINEAR>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-            break;
-          case EK_FINAL_RGB:
-            epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-            break;
-          default:
-            epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-            break;
+        // The layer's N is produced as two 128-column halves; half 0's epilogue overlaps half 1's MMAs, and
+        // the next layer's first K blocks can start as soon as half 0 has been published.
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&acc_full[2 * g + h], acc_phase, err_flag, 5);
+          tc_fence_after();
+          if (h == 1 && (L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
+            mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
+            bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
+                     &in_full[g]);
+          }
+          if (h < L.n_half) {
+            constexpr int span = CW;
+            const int c0 = h * 128 + sub * CW;
+            switch (kind) {
+              case EK_ACT_RELU:
+                epilogue_layer<NSPLIT, EK_ACT_RELU>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              case EK_ACT_RELU_ALPHA:
+                epilogue_layer<NSPLIT, EK_ACT_RELU_ALPHA>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              case EK_ACT_LINEAR:
+                epilogue_layer<NSPLIT, EK_ACT_LINEAR>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              case EK_FINAL_RGB:
+                epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              default:
+                epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+            }
+            if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
+          }
+          if (l + 1 < prog.n_layers) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&act_ready[2 * g + h]);
+          }
         }
+        acc_phase ^= 1;
         if (L.flags & LF_FINAL_RGB) {
-          if (grow < rows) {
+          // The QW warps of a lane quarter hold partial alpha / rgb dot products over their column slices:
+          // combine them through shared memory (the slot's hidden blocks are dead once this layer's MMAs
+          // have completed) and let the sub == 0 warp write the row.
+          if (QW > 1) {
+            float4* scratch = reinterpret_cast<float4*>(act_ptr(g, 0, prog.hid_blk0));
+            if (sub > 0) scratch[(sub - 1) * kTileM + row_in_tile] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(EW * 32) : "memory");
+            if (sub == 0) {
+#pragma unroll
+              for (int q = 1; q < QW; ++q) {
+                const float4 p = scratch[(q - 1) * kTileM + row_in_tile];
+                rgb[0] += p.x;
+                rgb[1] += p.y;
+                rgb[2] += p.z;
+                alpha += p.w;
+              }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(EW * 32) : "memory");
+          }
+          if (sub == 0 && grow < rows) {
             const float ab = prog.side[prog.alpha_b_off];
             const float b0 = prog.side[prog.rgb_b_off], b1 = prog.side[prog.rgb_b_off + 1], b2 = prog.side[prog.rgb_b_off + 2];
             reinterpret_cast<float4*>(out)[grow] = make_float4(rgb[0] + b0, rgb[1] + b1, rgb[2] + b2, alpha + ab);
           }
-        }
-        if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
-        if (l + 1 < prog.n_layers) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&act_ready[g]);
         }
       }
     }

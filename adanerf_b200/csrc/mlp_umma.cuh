@@ -6,7 +6,7 @@
 //   * activations never leave the SM: the fp32 accumulator lives in TMEM, the epilogue warps read it
 //     with tcgen05.ld, add bias / ReLU, round to bf16 (optionally a hi+lo split) and write the next
 //     layer's A operand straight into swizzled shared memory,
-//   * warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one elected thread), warps 2..9 =
+//   * warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one elected thread), warps 2..17 =
 //     epilogue.  With NG = 2 two tiles ping-pong per CTA (tile A's epilogue overlaps tile B's MMAs).
 //
 // NSPLIT = 2 is the split-precision mode of the sampling network: x = hi + lo (both bf16) for
@@ -20,7 +20,7 @@ namespace adn {
 constexpr int kTileM = 128;
 constexpr int kBlkBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B block
 constexpr int kMaxLayers = 12;
-constexpr int kMlpThreads = 320;  // 10 warps
+constexpr int kMlpThreads = 576;  // 18 warps: producer, MMA issuer, 16 epilogue warps
 constexpr int kSideFloats = 3200; // fp32 side parameters (biases, alpha / rgb heads) carried in the kernel parameters
 
 enum : uint8_t {
@@ -48,6 +48,7 @@ struct MlpProgram {
   int32_t n_layers;
   int32_t in0_blk, in0_nblk;  // tile-start input: destination block, number of blocks (per term)
   int32_t in1_blk;            // 2nd input destination block
+  int32_t hid_blk0;           // first hidden-activation block (blocks below it hold tile inputs)
   uint32_t in_tile_stride;    // bytes per tile in the packed input buffer
   uint32_t in0_off, in0_lo_off, in1_off;
   uint32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;  // float offsets in `side`
