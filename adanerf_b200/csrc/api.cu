@@ -121,12 +121,12 @@ struct Seg {
   int col0, valid;
 };
 
-// Packs one layer's weights W [n_out, k_in] into the ring-stage stream: for each 128-row N half, for each
-// K block (Seg): a [128 x 64] K-major SWIZZLE_128B bf16 tile (hi), followed by the lo tile when nsplit == 2.
+// Packs one layer's weights W [n_out, k_in] into the ring-stage stream: for each K block (Seg), for each
+// 128-row N half: a [128 x 64] K-major SWIZZLE_128B bf16 tile (hi), followed by the lo tile when nsplit == 2.
 void pack_layer(const float* W, int n_out, int k_in, const std::vector<Seg>& segs, int nsplit, std::vector<uint8_t>& blob) {
   const int n_half = (n_out + 127) / 128;
-  for (int nh = 0; nh < n_half; ++nh) {       // N half outermost: half 0's accumulator completes first
-    for (const Seg& sg : segs) {
+  for (const Seg& sg : segs) {
+    for (int nh = 0; nh < n_half; ++nh) {
       const size_t base = blob.size();
       blob.resize(base + size_t(nsplit) * kBlkBytes, 0);
       for (int n = 0; n < 128; ++n) {
@@ -318,9 +318,11 @@ adn_status build_net1(adn_ctx* ctx) {
       W = fw;
       B = fb;
     } else {  // views_linears.0 on cat[feature, views] (models.py:266-269) + rgb_linear in the epilogue
-      segs = {{0, 64}, {64, 64}, {128, 64}, {192, 64}, {256, 27}};
-      const uint8_t blk[5] = {1, 2, 3, 4, 0};
-      std::memcpy(L.a_blk, blk, 5);
+      // a sixth all-zero K block keeps the ring's stage count per layer even: the 256-wide layers read
+      // their B operand from aligned stage PAIRS
+      segs = {{0, 64}, {64, 64}, {128, 64}, {192, 64}, {256, 27}, {0, 0}};
+      const uint8_t blk[6] = {1, 2, 3, 4, 0, 0};
+      std::memcpy(L.a_blk, blk, 6);
       L.flags = LF_RELU | LF_FINAL_RGB | LF_WAIT_IN;
       L.n_half = 1;
       W = vw;

@@ -165,20 +165,21 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   constexpr int NB = Cfg::kNB;
   constexpr int STAGES = Cfg::kStages;
   constexpr int STAGE_BYTES = Cfg::kStageBytes;
-  constexpr int EW = 16 / NG;  // epilogue warps per tile slot
+  constexpr int EW = 16 / NG;   // epilogue warps per tile slot
   constexpr int QW = EW / 4;    // warps sharing one TMEM lane quarter (they split the columns)
   constexpr int CW = 128 / QW;  // accumulator columns per warp and N half
+  constexpr int kProducerWarp = 16, kMmaWarp = 17;   // highest warp ids: the issue arbiter favours them
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* act = smem;                                                   // [NG][NSPLIT][NB] blocks
   uint8_t* ring = act + size_t(NG) * NSPLIT * NB * kBlkBytes;            // [STAGES] stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(STAGES) * STAGE_BYTES);
-  uint64_t* w_full = bars;                     // [STAGES]
-  uint64_t* w_empty = bars + STAGES;           // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;      // [NG][2]  accumulator half (128 columns) complete
-  uint64_t* act_ready = acc_full + 2 * NG;     // [NG][2]  epilogue of that half done (TMEM half free, A blocks written)
-  uint64_t* in_full = act_ready + 2 * NG;      // [NG]
+  uint64_t* w_full = bars;                 // [STAGES]
+  uint64_t* w_empty = bars + STAGES;       // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;  // [NG]  all MMAs of the layer have retired
+  uint64_t* act_ready = acc_full + NG;     // [NG]  epilogue done: TMEM free, next layer's A operand written
+  uint64_t* in_full = act_ready + NG;      // [NG]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + NG);
 
   // warp index through a lane-0 broadcast: tells the compiler it is warp uniform, so the role branches
@@ -195,15 +196,13 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       mbar_init(&w_empty[s], 1);
     }
     for (int g = 0; g < NG; ++g) {
-      for (int h = 0; h < 2; ++h) {
-        mbar_init(&acc_full[2 * g + h], 1);
-        mbar_init(&act_ready[2 * g + h], EW);
-      }
+      mbar_init(&acc_full[g], 1);
+      mbar_init(&act_ready[g], EW);
       mbar_init(&in_full[g], 1);
     }
     mbar_fence_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -219,7 +218,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     return (iter * gridDim.x + blockIdx.x) * NG + g;
   };
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================================================================== weight producer
     if (lane == 0) {
       int stage = 0;
@@ -245,68 +244,78 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ========================================================================== MMA issuer
     // The whole warp walks the schedule converged (every quantity below is warp uniform, so the
     // descriptors live in uniform registers); one elected lane issues the tcgen05 instructions.
-    constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    // With plain bf16 (NSPLIT == 1) a 256-wide layer is issued as N = 256 MMAs whose B operand spans the two
+    // adjacent ring stages (kb, half 0) and (kb, half 1): half the instructions per flop of N = 128.
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128);
+    constexpr uint32_t idesc256 = make_idesc_bf16(128, 256);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t in_phase[NG], ar_phase[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) in_phase[g] = ar_phase[g] = 0;
-    const uint32_t ring_u32 = smem_u32(ring);
-    const uint64_t desc_hi = make_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // constant upper half
+    const uint64_t desc_hi = make_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // constant upper word
     const uint32_t desc_lo_const = uint32_t(make_desc_sw128(0) & 0xFFFF0000ull);
-    auto desc_of = [&](uint32_t addr) -> uint64_t {
-      return desc_hi | uint64_t(desc_lo_const | ((addr & 0x3FFFFu) >> 4));
-    };
+    // low descriptor word of an address: a K step of 16 elements (+32 B) is "+2" on this word
+    auto lo_of = [&](uint32_t addr) -> uint32_t { return desc_lo_const | (addr >> 4); };
+    const uint32_t ring_lo = lo_of(smem_u32(ring));
+    const uint32_t act_lo0 = lo_of(smem_u32(act));
+    auto desc = [&](uint32_t lo) -> uint64_t { return desc_hi | uint64_t(lo); };
     for (long long iter = 0;; ++iter) {
       if (tile_of(iter, 0) >= n_tiles) break;
       for (int l = 0; l < prog.n_layers; ++l) {
         const MlpLayer& L = prog.layers[l];
+        const bool wide = (NSPLIT == 1) && (L.n_half == 2);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           if (tile_of(iter, g) >= n_tiles) continue;
-          // Per layer exactly one phase of act_ready[g][0..1] is consumed: half h of the previous layer's
-          // epilogue frees TMEM columns [128h, 128h+128) and publishes hidden blocks hid_blk0 + 2h, +1.
-          bool waited[2] = {false, false};
-          bool in_waited = false;
-          auto ensure = [&](int h) {
-            if (!waited[h]) {
-              mbar_wait(&act_ready[2 * g + h], ar_phase[g], err_flag, 3);
+          if (l == 0 || (L.flags & LF_WAIT_IN)) {
+            mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
+            in_phase[g] ^= 1;
+          }
+          mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
+          ar_phase[g] ^= 1;
+          tc_fence_after();
+          const uint32_t a_g = act_lo0 + uint32_t(g * NSPLIT * NB) * (kBlkBytes >> 4);
+          const uint32_t d0 = tmem_base + uint32_t(g * 256);
+          for (int kb = 0; kb < L.n_kb; ++kb) {
+            const uint32_t a_hi = a_g + uint32_t(L.a_blk[kb]) * (kBlkBytes >> 4);
+            const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * (kBlkBytes >> 4);
+            if (wide) {
+              mbar_wait(&w_full[stage], phase, err_flag, 4);
+              mbar_wait(&w_full[stage + 1], phase, err_flag, 4);
               tc_fence_after();
-              waited[h] = true;
-            }
-          };
-          const uint32_t act_g = smem_u32(act) + uint32_t(g * NSPLIT * NB) * kBlkBytes;
-          for (int nh = 0; nh < 2; ++nh) {
-            ensure(nh);
-            if (nh < L.n_half) {
-              for (int kb = 0; kb < L.n_kb; ++kb) {
-                const int blk = L.a_blk[kb];
-                if (blk >= prog.hid_blk0 && l > 0) {
-                  ensure((blk - prog.hid_blk0) >> 1);
-                } else if (!in_waited && (l == 0 || (L.flags & LF_WAIT_IN))) {
-                  mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
-                  in_phase[g] ^= 1;
-                  in_waited = true;
-                }
-                const uint32_t a_hi = act_g + uint32_t(blk) * kBlkBytes;
-                const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * kBlkBytes;
+              const uint32_t b = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc256, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&w_empty[stage]);
+                umma_commit(&w_empty[stage + 1]);
+              }
+              __syncwarp();
+              stage += 2;
+              if (stage >= STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            } else {
+              for (int nh = 0; nh < L.n_half; ++nh) {
                 mbar_wait(&w_full[stage], phase, err_flag, 4);
                 tc_fence_after();
-                const uint32_t b_hi = ring_u32 + uint32_t(stage) * STAGE_BYTES;
-                const uint32_t b_lo = b_hi + kBlkBytes;
-                const uint32_t d = tmem_base + uint32_t(g * 256 + nh * 128);
+                const uint32_t b_hi = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
+                const uint32_t b_lo = b_hi + (kBlkBytes >> 4);
+                const uint32_t d = d0 + uint32_t(nh * 128);
                 if (elect_one()) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                    umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_hi + k * 32), idesc, acc);
+                    umma_bf16(d, desc(a_hi + 2 * k), desc(b_hi + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
                     if (NSPLIT == 2) {
-                      umma_bf16(d, desc_of(a_lo + k * 32), desc_of(b_hi + k * 32), idesc, 1u);
-                      umma_bf16(d, desc_of(a_hi + k * 32), desc_of(b_lo + k * 32), idesc, 1u);
+                      umma_bf16(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
+                      umma_bf16(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
                     }
                   }
                   umma_commit(&w_empty[stage]);
@@ -318,16 +327,15 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
                 }
               }
             }
-            if (elect_one()) umma_commit(&acc_full[2 * g + nh]);
-            __syncwarp();
           }
-          ar_phase[g] ^= 1;
+          if (elect_one()) umma_commit(&acc_full[g]);
+          __syncwarp();
         }
       }
     }
   } else {
     // ============================================================================ epilogue
-    const int ew = warp - 2;                       // 0..15
+    const int ew = warp;                           // 0..15
     const int g = ew / EW;                         // tile slot
     const int e = ew % EW;                         // index inside the slot's warp set
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
@@ -350,10 +358,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       // accumulator columns and activation buffers of this slot are free for layer 0
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&act_ready[2 * g + 0]);
-        mbar_arrive(&act_ready[2 * g + 1]);
-      }
+      if (lane == 0) mbar_arrive(&act_ready[g]);
 
       float alpha = 0.0f;
       float rgb[3] = {0.0f, 0.0f, 0.0f};
@@ -361,49 +366,38 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         const MlpLayer& L = prog.layers[l];
         const int kind = epilogue_kind(L.flags);
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(g * 256);
-        // The layer's N is produced as two 128-column halves; half 0's epilogue overlaps half 1's MMAs, and
-        // the next layer's first K blocks can start as soon as half 0 has been published.
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&acc_full[2 * g + h], acc_phase, err_flag, 5);
-          tc_fence_after();
-          if (h == 1 && (L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
-            mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
-            bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
-                     &in_full[g]);
-          }
-          if (h < L.n_half) {
-            constexpr int span = CW;
-            const int c0 = h * 128 + sub * CW;
-            switch (kind) {
-              case EK_ACT_RELU:
-                epilogue_layer<NSPLIT, EK_ACT_RELU>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-                break;
-              case EK_ACT_RELU_ALPHA:
-                epilogue_layer<NSPLIT, EK_ACT_RELU_ALPHA>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-                break;
-              case EK_ACT_LINEAR:
-                epilogue_layer<NSPLIT, EK_ACT_LINEAR>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-                break;
-              case EK_FINAL_RGB:
-                epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-                break;
-              default:
-                epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, span, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-                break;
-            }
-            if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
-          }
-          if (l + 1 < prog.n_layers) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&act_ready[2 * g + h]);
+        mbar_wait(&acc_full[g], acc_phase, err_flag, 5);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
+          mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
+          bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
+                   &in_full[g]);
+        }
+        for (int h = 0; h < L.n_half; ++h) {
+          const int c0 = h * 128 + sub * CW;
+          switch (kind) {
+            case EK_ACT_RELU:
+              epilogue_layer<NSPLIT, EK_ACT_RELU>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+            case EK_ACT_RELU_ALPHA:
+              epilogue_layer<NSPLIT, EK_ACT_RELU_ALPHA>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+            case EK_ACT_LINEAR:
+              epilogue_layer<NSPLIT, EK_ACT_LINEAR>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+            case EK_FINAL_RGB:
+              epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+            default:
+              epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
           }
         }
-        acc_phase ^= 1;
         if (L.flags & LF_FINAL_RGB) {
           // The QW warps of a lane quarter hold partial alpha / rgb dot products over their column slices:
           // combine them through shared memory (the slot's hidden blocks are dead once this layer's MMAs
-          // have completed) and let the sub == 0 warp write the row.
+          // have retired) and let the sub == 0 warp write the row.
           if (QW > 1) {
             float4* scratch = reinterpret_cast<float4*>(act_ptr(g, 0, prog.hid_blk0));
             if (sub > 0) scratch[(sub - 1) * kTileM + row_in_tile] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
@@ -426,13 +420,19 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
             reinterpret_cast<float4*>(out)[grow] = make_float4(rgb[0] + b0, rgb[1] + b1, rgb[2] + b2, alpha + ab);
           }
         }
+        if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
+        if (l + 1 < prog.n_layers) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&act_ready[g]);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -20,7 +20,7 @@ namespace adn {
 constexpr int kTileM = 128;
 constexpr int kBlkBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B block
 constexpr int kMaxLayers = 12;
-constexpr int kMlpThreads = 576;  // 18 warps: producer, MMA issuer, 16 epilogue warps
+constexpr int kMlpThreads = 576;  // 18 warps: 16 epilogue, weight producer, MMA issuer
 constexpr int kSideFloats = 3200; // fp32 side parameters (biases, alpha / rgb heads) carried in the kernel parameters
 
 enum : uint8_t {
@@ -37,11 +37,11 @@ struct MlpLayer {
   uint32_t w_off;     // byte offset of this layer's packed weight stages (consumption order)
   uint32_t bias_off;  // float offset of the bias vector in MlpProgram::side
   uint8_t n_kb;       // number of 64-wide K blocks
-  uint8_t a_blk[5];   // activation block index per K block
+  uint8_t a_blk[6];   // activation block index per K block
   uint8_t n_half;     // N / 128  (1 or 2)
   uint8_t flags;
   uint8_t out_blk0;   // first activation block the epilogue writes
-  uint8_t pad[3];
+  uint8_t pad[2];
 };
 
 struct MlpProgram {
