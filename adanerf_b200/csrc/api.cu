@@ -56,6 +56,8 @@ struct adn_ctx {
   Buf tiles0, raw0, x0, ray_o, ray_d, dirs, count, offset, rayidx, zbuf, zpbuf, tiles1, raw1, s2scratch, rgb, rgba, x1;
   long long* d_total = nullptr;
   int* d_err = nullptr;
+  long long* d_trace = nullptr;   // debug timeline of the MLP kernels (option "trace")
+  int trace_net = -1;
   // pinned staging for the *_host entry points
   Buf h_in, h_out, h_ns;
   cudaStream_t own_stream = nullptr;
@@ -318,11 +320,9 @@ adn_status build_net1(adn_ctx* ctx) {
       W = fw;
       B = fb;
     } else {  // views_linears.0 on cat[feature, views] (models.py:266-269) + rgb_linear in the epilogue
-      // a sixth all-zero K block keeps the ring's stage count per layer even: the 256-wide layers read
-      // their B operand from aligned stage PAIRS
-      segs = {{0, 64}, {64, 64}, {128, 64}, {192, 64}, {256, 27}, {0, 0}};
-      const uint8_t blk[6] = {1, 2, 3, 4, 0, 0};
-      std::memcpy(L.a_blk, blk, 6);
+      segs = {{0, 64}, {64, 64}, {128, 64}, {192, 64}, {256, 27}};
+      const uint8_t blk[5] = {1, 2, 3, 4, 0};
+      std::memcpy(L.a_blk, blk, 5);
       L.flags = LF_RELU | LF_FINAL_RGB | LF_WAIT_IN;
       L.n_half = 1;
       W = vw;
@@ -416,7 +416,8 @@ int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
 adn_status run_mlp(adn_ctx* ctx, int id, const uint8_t* tiles, float* out, const long long* rows_dev, long long rows,
                    cudaStream_t st) {
   Net& n = ctx->net[id];
-  cudaError_t e = launch_mlp(n.nsplit, n.ng, n.prog, n.d_wblob, tiles, out, rows_dev, rows, ctx->d_err, ctx->num_sms, st);
+  cudaError_t e = launch_mlp(n.nsplit, n.ng, n.prog, n.d_wblob, tiles, out, rows_dev, rows, ctx->d_err, ctx->num_sms, st,
+                             ctx->trace_net == id ? ctx->d_trace : nullptr);
   if (e != cudaSuccess) return cuda_fail(ctx, e, id == 0 ? "launch sampling MLP" : "launch shading MLP");
   ctx->stats.kernel_launches++;
   return ADN_OK;
@@ -620,6 +621,7 @@ void adn_destroy(adn_ctx* ctx) {
   if (ctx->d_zlut_dense) cudaFree(ctx->d_zlut_dense);
   if (ctx->d_total) cudaFree(ctx->d_total);
   if (ctx->d_err) cudaFree(ctx->d_err);
+  if (ctx->d_trace) cudaFree(ctx->d_trace);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -657,6 +659,12 @@ adn_status adn_set_option(adn_ctx* ctx, const char* name, int64_t value) {
   }
   if (n == "profile") {
     ctx->profile = value != 0;
+    return ADN_OK;
+  }
+  if (n == "trace") {   // debug: value = net id to trace (0 / 1), -1 = off
+    ctx->trace_net = int(value);
+    if (value >= 0 && !ctx->d_trace) ADN_CUDA(ctx, cudaMalloc(&ctx->d_trace, sizeof(long long) * 65536));
+    if (ctx->d_trace) ADN_CUDA(ctx, cudaMemset(ctx->d_trace, 0, sizeof(long long) * 65536));
     return ADN_OK;
   }
   if (n == "mlp0_terms") {
@@ -857,6 +865,14 @@ adn_status adn_stage5_composite(adn_ctx* ctx, const float* d_raw1, const float* 
   ADN_CUDA(ctx, launch_stage5(d_raw1, d_zp, d_z, nullptr, d_offset, d_count, n_rays, K, 0, d_rgb, nullptr, d_weights,
                               d_depth_map, static_cast<cudaStream_t>(stream)));
   ctx->stats.kernel_launches++;
+  return ADN_OK;
+}
+
+// Debug only (not part of the public header): copies the MLP timeline recorded after adn_set_option("trace", net).
+adn_status adn_debug_read_trace(adn_ctx* ctx, long long* out, int64_t n_words) {
+  if (!ctx || !out || !ctx->d_trace || n_words < 2 || n_words > 65536) return ADN_ERR_INVALID;
+  ADN_CUDA(ctx, cudaDeviceSynchronize());
+  ADN_CUDA(ctx, cudaMemcpy(out, ctx->d_trace, sizeof(long long) * n_words, cudaMemcpyDeviceToHost));
   return ADN_OK;
 }
 

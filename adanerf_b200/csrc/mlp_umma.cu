@@ -10,8 +10,10 @@ namespace adn {
 template <int NSPLIT>
 struct MlpCfg {
   static constexpr int kNB = (NSPLIT == 2) ? 4 : 5;            // activation blocks per slot and term
-  static constexpr int kStages = (NSPLIT == 2) ? 3 : 4;        // weight ring depth
-  static constexpr int kStageBytes = NSPLIT * kBlkBytes;       // [128 x 64] hi (+ lo)
+  // weight ring: split precision: 3 stages of [128 x 64] hi + lo (one stage per K block and N half);
+  // plain bf16: 2 stages of [256 x 64] (one stage per K block: both N halves, one barrier round trip per 4 MMAs)
+  static constexpr int kStages = (NSPLIT == 2) ? 3 : 2;
+  static constexpr int kStageBytes = 2 * kBlkBytes;
 };
 
 template <int NSPLIT, int NG>
@@ -160,7 +162,7 @@ template <int NSPLIT, int NG>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict__ wblob,
                 const uint8_t* __restrict__ in_tiles, float* __restrict__ out,
-                const long long* __restrict__ rows_dev, long long rows_host, int* err_flag) {
+                const long long* __restrict__ rows_dev, long long rows_host, int* err_flag, long long* trace) {
   using Cfg = MlpCfg<NSPLIT>;
   constexpr int NB = Cfg::kNB;
   constexpr int STAGES = Cfg::kStages;
@@ -168,7 +170,8 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   constexpr int EW = 16 / NG;   // epilogue warps per tile slot
   constexpr int QW = EW / 4;    // warps sharing one TMEM lane quarter (they split the columns)
   constexpr int CW = 128 / QW;  // accumulator columns per warp and N half
-  constexpr int kProducerWarp = 16, kMmaWarp = 17;   // highest warp ids: the issue arbiter favours them
+  constexpr int kProducerWarp = 16, kHelperWarp = 17, kMmaWarp = 18;   // highest warp ids: favoured by the issue arbiter
+  constexpr int kBarSlot = 3, kBarStage = 5;   // named barrier ids (1, 2 are used by the epilogue warps)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -217,6 +220,19 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   auto tile_of = [&](long long iter, int g) -> long long {
     return (iter * gridDim.x + blockIdx.x) * NG + g;
   };
+  // Optional timeline (debug): a few warps of CTA 0 record (clock, code) pairs into private regions of `trace`
+  // (region r: words [r*8192, (r+1)*8192), word 0 = count); code = slot<<16 | layer<<8 | event.  Off (nullptr)
+  // in normal operation.
+  const bool tracing = (trace != nullptr) && (blockIdx.x == 0);
+  int tr_n = 0;
+  auto tr = [&](int region, int g, int l, int ev) {
+    if (tracing && tr_n < 4000) {
+      long long* base = trace + region * 8192;
+      base[2 + 2 * tr_n] = clock64();
+      base[3 + 2 * tr_n] = (long long)((g << 16) | (l << 8) | ev);
+      base[0] = ++tr_n;
+    }
+  };
 
   if (warp == kProducerWarp) {
     // ===================================================================== weight producer
@@ -227,18 +243,58 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         if (tile_of(iter, 0) >= n_tiles) break;
         for (int l = 0; l < prog.n_layers; ++l) {
           const MlpLayer& L = prog.layers[l];
-          const int n_st = int(L.n_kb) * int(L.n_half);
+          // split precision: one stage per (K block, N half) = hi + lo tiles; plain bf16: one stage per K block
+          // holding the layer's 1 or 2 N halves back to back
+          const int n_st = (NSPLIT == 2) ? int(L.n_kb) * int(L.n_half) : int(L.n_kb);
+          const uint32_t st_bytes = (NSPLIT == 2) ? uint32_t(STAGE_BYTES) : uint32_t(L.n_half) * kBlkBytes;
           for (int g = 0; g < NG; ++g) {
             if (tile_of(iter, g) >= n_tiles) continue;
             const uint8_t* src = wblob + L.w_off;
             for (int i = 0; i < n_st; ++i) {
               mbar_wait(&w_empty[stage], phase ^ 1, err_flag, 1);
-              mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
-              bulk_g2s(ring + size_t(stage) * STAGE_BYTES, src + size_t(i) * STAGE_BYTES, STAGE_BYTES, &w_full[stage]);
+              mbar_arrive_expect_tx(&w_full[stage], st_bytes);
+              bulk_g2s(ring + size_t(stage) * STAGE_BYTES, src + size_t(i) * st_bytes, st_bytes, &w_full[stage]);
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1;
               }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kHelperWarp) {
+    // =================================================================== barrier helper
+    // Walks the same schedule as the MMA issuer one step ahead and turns every mbarrier round trip
+    // (try_wait is ~100-200 cycles even when the phase has already completed) into a named-barrier
+    // arrival, which the issuer consumes with a ~tens-of-cycles bar.sync: the issuer's serial chain per
+    // K block shrinks to "bar.sync, issue 4 MMAs, commit".
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t in_phase[NG], ar_phase[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) in_phase[g] = ar_phase[g] = 0;
+    for (long long iter = 0;; ++iter) {
+      if (tile_of(iter, 0) >= n_tiles) break;
+      for (int l = 0; l < prog.n_layers; ++l) {
+        const MlpLayer& L = prog.layers[l];
+        const int n_st = (NSPLIT == 2) ? int(L.n_kb) * int(L.n_half) : int(L.n_kb);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (tile_of(iter, g) >= n_tiles) continue;
+          if (l == 0 || (L.flags & LF_WAIT_IN)) {
+            mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
+            in_phase[g] ^= 1;
+          }
+          mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
+          ar_phase[g] ^= 1;
+          named_bar_arrive(kBarSlot + g, 64);
+          for (int i = 0; i < n_st; ++i) {
+            mbar_wait(&w_full[stage], phase, err_flag, 4);
+            named_bar_arrive(kBarStage + stage, 64);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
             }
           }
         }
@@ -253,10 +309,6 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     constexpr uint32_t idesc128 = make_idesc_bf16(128, 128);
     constexpr uint32_t idesc256 = make_idesc_bf16(128, 256);
     int stage = 0;
-    uint32_t phase = 0;
-    uint32_t in_phase[NG], ar_phase[NG];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) in_phase[g] = ar_phase[g] = 0;
     const uint64_t desc_hi = make_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // constant upper word
     const uint32_t desc_lo_const = uint32_t(make_desc_sw128(0) & 0xFFFF0000ull);
     // low descriptor word of an address: a K step of 16 elements (+32 B) is "+2" on this word
@@ -269,42 +321,46 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       for (int l = 0; l < prog.n_layers; ++l) {
         const MlpLayer& L = prog.layers[l];
         const bool wide = (NSPLIT == 1) && (L.n_half == 2);
+        // this layer's A block indices packed 4 bits each: the issue loop extracts them with a shift instead
+        // of a dependent constant-bank load per K block
+        uint32_t blks = 0;
+#pragma unroll
+        for (int kb = 0; kb < 6; ++kb) blks |= uint32_t(L.a_blk[kb] & 15) << (4 * kb);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           if (tile_of(iter, g) >= n_tiles) continue;
-          if (l == 0 || (L.flags & LF_WAIT_IN)) {
-            mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
-            in_phase[g] ^= 1;
-          }
-          mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
-          ar_phase[g] ^= 1;
+          if (lane == 0) tr(0, g, l, 0);
+          named_bar_sync(kBarSlot + g, 64);   // helper has seen in_full / act_ready of this slot
           tc_fence_after();
-          const uint32_t a_g = act_lo0 + uint32_t(g * NSPLIT * NB) * (kBlkBytes >> 4);
+          if (lane == 0) tr(0, g, l, 1);
           const uint32_t d0 = tmem_base + uint32_t(g * 256);
           for (int kb = 0; kb < L.n_kb; ++kb) {
-            const uint32_t a_hi = a_g + uint32_t(L.a_blk[kb]) * (kBlkBytes >> 4);
+            const uint32_t a_hi = act_lo0 + (uint32_t(g * NSPLIT * NB) + ((blks >> (4 * kb)) & 15u)) * (kBlkBytes >> 4);
             const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * (kBlkBytes >> 4);
-            if (wide) {
-              mbar_wait(&w_full[stage], phase, err_flag, 4);
-              mbar_wait(&w_full[stage + 1], phase, err_flag, 4);
+            if (NSPLIT == 1) {
+              if (lane == 0 && l == 2) tr(0, g, kb, 5);
+              named_bar_sync(kBarStage + stage, 64);   // helper has seen w_full[stage]
               tc_fence_after();
+              if (lane == 0 && l == 2) tr(0, g, kb, 6);
               const uint32_t b = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
               if (elect_one()) {
+                if (wide) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc256, (kb > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc256, (kb > 0 || k > 0) ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&w_empty[stage]);
-                umma_commit(&w_empty[stage + 1]);
               }
               __syncwarp();
-              stage += 2;
-              if (stage >= STAGES) {
-                stage = 0;
-                phase ^= 1;
-              }
+              if (lane == 0 && l == 2) tr(0, g, kb, 7);
+              stage ^= 1;
             } else {
               for (int nh = 0; nh < L.n_half; ++nh) {
-                mbar_wait(&w_full[stage], phase, err_flag, 4);
+                named_bar_sync(kBarStage + stage, 64);
                 tc_fence_after();
                 const uint32_t b_hi = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
                 const uint32_t b_lo = b_hi + (kBlkBytes >> 4);
@@ -313,23 +369,19 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     umma_bf16(d, desc(a_hi + 2 * k), desc(b_hi + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
-                    if (NSPLIT == 2) {
-                      umma_bf16(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
-                      umma_bf16(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
-                    }
+                    umma_bf16(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
+                    umma_bf16(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
                   }
                   umma_commit(&w_empty[stage]);
                 }
                 __syncwarp();
-                if (++stage == STAGES) {
-                  stage = 0;
-                  phase ^= 1;
-                }
+                if (++stage == STAGES) stage = 0;
               }
             }
           }
           if (elect_one()) umma_commit(&acc_full[g]);
           __syncwarp();
+          if (lane == 0) tr(0, g, l, 2);
         }
       }
     }
@@ -369,6 +421,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         mbar_wait(&acc_full[g], acc_phase, err_flag, 5);
         acc_phase ^= 1;
         tc_fence_after();
+        if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 3);
         if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
           mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
           bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
@@ -421,6 +474,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
           }
         }
         if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
+        if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 4);
         if (l + 1 < prog.n_layers) {
           tc_fence_before();
           __syncwarp();
@@ -489,7 +543,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, long long rows_hos
 template <int NSPLIT, int NG>
 static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles,
                                 float* out, const long long* rows_dev, long long rows_host, int* err_flag, int num_sms,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, long long* trace) {
   static bool attr_set = false;
   const size_t smem = mlp_smem_layout_bytes<NSPLIT, NG>();
   if (!attr_set) {
@@ -504,16 +558,16 @@ static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, co
     if (need < grid) grid = int(need < 1 ? 1 : need);
   }
   mlp_umma_kernel<NSPLIT, NG><<<grid, kMlpThreads, smem, stream>>>(prog, wblob, in_tiles, out, rows_dev, rows_host,
-                                                                   err_flag);
+                                                                   err_flag, trace);
   return cudaGetLastError();
 }
 
 cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host, int* err_flag,
-                       int num_sms, cudaStream_t stream) {
-  if (nsplit == 2) return launch_mlp_t<2, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
-  if (ng == 2) return launch_mlp_t<1, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
-  return launch_mlp_t<1, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream);
+                       int num_sms, cudaStream_t stream, long long* trace) {
+  if (nsplit == 2) return launch_mlp_t<2, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+  if (ng == 2) return launch_mlp_t<1, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+  return launch_mlp_t<1, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
 }
 
 cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat, const InputLayout& lay,

@@ -20,7 +20,7 @@ namespace adn {
 constexpr int kTileM = 128;
 constexpr int kBlkBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B block
 constexpr int kMaxLayers = 12;
-constexpr int kMlpThreads = 576;  // 18 warps: 16 epilogue, weight producer, MMA issuer
+constexpr int kMlpThreads = 608;  // 19 warps: 16 epilogue, weight producer, barrier helper, MMA issuer
 constexpr int kSideFloats = 3200; // fp32 side parameters (biases, alpha / rgb heads) carried in the kernel parameters
 
 enum : uint8_t {
@@ -75,7 +75,7 @@ size_t mlp_smem_bytes(int nsplit, int ng);
 // Launchers (defined in mlp_umma.cu).  rows_dev may be null (then rows_host is used).
 cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host,
-                       int* err_flag, int num_sms, cudaStream_t stream);
+                       int* err_flag, int num_sms, cudaStream_t stream, long long* trace = nullptr);
 cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat,
                              const InputLayout& lay, uint8_t* tiles, cudaStream_t stream);
 
