@@ -868,6 +868,24 @@ adn_status adn_stage5_composite(adn_ctx* ctx, const float* d_raw1, const float* 
   return ADN_OK;
 }
 
+adn_status adn_probe_export_dir(const char* dir, adn_scene* scene_out, float* thr_out, int* k_out, int* n_tensors_out) {
+  if (!dir) return ADN_ERR_INVALID;
+  adn::ExportDir ex;
+  std::string err;
+  if (!adn::load_export_dir(dir, ex, err)) {
+    std::fprintf(stderr, "adanerf_b200: %s\n", err.c_str());
+    return ADN_ERR_IO;
+  }
+  if (scene_out) *scene_out = ex.scene;
+  if (thr_out) *thr_out = ex.threshold;
+  if (k_out) *k_out = ex.num_samples;
+  if (n_tensors_out) {
+    n_tensors_out[0] = int(ex.nets[0].size());
+    n_tensors_out[1] = int(ex.nets[1].size());
+  }
+  return ADN_OK;
+}
+
 // Debug only (not part of the public header): copies the MLP timeline recorded after adn_set_option("trace", net).
 adn_status adn_debug_read_trace(adn_ctx* ctx, long long* out, int64_t n_words) {
   if (!ctx || !out || !ctx->d_trace || n_words < 2 || n_words > 65536) return ADN_ERR_INVALID;

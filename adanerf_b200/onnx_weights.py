@@ -91,3 +91,61 @@ def read_onnx_initializers(path):
                     if arr is not None:
                         out[name] = arr
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Writer (tests / tooling): emits a ModelProto whose graph carries only fp32 initialisers with raw_data,
+# i.e. the part of the reference's export (src/export.py:81-83) that the renderer consumes.
+def _enc_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _field(fn, wt, payload):
+    key = _enc_varint((fn << 3) | wt)
+    if wt == 0:
+        return key + _enc_varint(payload)
+    return key + _enc_varint(len(payload)) + payload
+
+
+def write_onnx_initializers(path, tensors):
+    """tensors: dict name -> float32 ndarray.  Layout: ModelProto{ir_version(1)=4, graph(7)=GraphProto{initializer(5)*}}."""
+    graph = b""
+    for name, arr in tensors.items():
+        a = np.ascontiguousarray(arr, dtype="<f4")
+        t = b"".join(_field(1, 0, int(d)) for d in a.shape)
+        t += _field(2, 0, 1)                         # data_type = FLOAT
+        t += _field(8, 2, name.encode("utf-8"))
+        t += _field(9, 2, a.tobytes())               # raw_data, little endian
+        graph += _field(5, 2, t)
+    model = _field(1, 0, 4) + _field(7, 2, graph)
+    with open(path, "wb") as f:
+        f.write(model)
+
+
+def write_export_dir(path, scene, sd0, sd1, thr, K):
+    """Writes {config.ini, dataset_info.txt, model0.onnx, model1.onnx} in the reference's export format
+    (src/export.py:28-93, src/train_data.py:180-195)."""
+    import os
+    os.makedirs(path, exist_ok=True)
+    as_np = lambda sd: {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in sd.items()}
+    write_onnx_initializers(os.path.join(path, "model0.onnx"), as_np(sd0))
+    write_onnx_initializers(os.path.join(path, "model1.onnx"), as_np(sd1))
+    with open(os.path.join(path, "dataset_info.txt"), "w") as f:
+        f.write(f"view_cell_center = {list(scene['view_cell_center'])}\n")
+        f.write(f"view_cell_size = {list(scene['view_cell_size'])}\n")
+        f.write(f"depth_range = {list(scene['depth_range'])}\n")
+        f.write(f"fov = {scene['fov']}\nfocal = 0.0\ncamera_scale = 1.0\nmax_depth = {scene['max_depth']}\n")
+    with open(os.path.join(path, "config.ini"), "w") as f:
+        f.write("posEnc = [nerf, nerf]\nposEncArgs = [10-4, 10-4]\ninFeatures = [SpherePosDir, RayMarchFromPoses]\n"
+                "outFeatures = [RawSigmoid, RGBARayMarch]\nrayMarchSampler = [none, FromClassifiedDepthAdaptive]\n"
+                "rayMarchNormalization = [InverseSqrtDistCentered, InverseSqrtDistCentered]\n"
+                f"numRaymarchSamples = [{K}, {K}]\ndepthTransform = log\nzNear = [0.001, 0.001]\nzFar = [1.0, 1.0]\n"
+                f"adaptiveSamplingThreshold = {thr}\nmultiDepthFeatures = [128, 128]\naccumulationMult = alpha\n")

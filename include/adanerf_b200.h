@@ -87,6 +87,11 @@ adn_status adn_set_weights(adn_ctx* ctx, int net_id, const adn_tensor_desc* tens
  * returned through thr_out / k_out (may be NULL). */
 adn_status adn_create_from_export_dir(adn_ctx** out, const char* dir, int device, float* thr_out, int* k_out);
 
+/* Host-only (no GPU needed): parses the export directory like adn_create_from_export_dir and returns the
+ * scene, threshold, K and the number of fp32 tensors found in model0.onnx / model1.onnx.  Replaces
+ * Config::load + Config::loadDatasetInfo (adanerf_real_time_viewer/src/config.cpp:270-344). */
+adn_status adn_probe_export_dir(const char* dir, adn_scene* scene_out, float* thr_out, int* k_out, int* n_tensors_out /*[2]*/);
+
 /* name: "chunk_rays" (rays per internal batch, 0 = auto), "profile" (0/1 per-stage event timing),
  * "mlp0_terms" (3 = bf16x3 split precision [default], 1 = plain bf16; parity experiments only). */
 adn_status adn_set_option(adn_ctx* ctx, const char* name, int64_t value);

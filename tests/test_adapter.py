@@ -1,0 +1,51 @@
+"""TrainConfig.inference drop-in (adanerf_b200.adapter) against the golden output of the reference's own
+inference() call on the same batch."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import case_weights, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+class _Batch:   # what SampleDataWrapper.get_batch_input returns (src/datasets.py:70-80)
+    def __init__(self, d):
+        self.d = d
+
+    def get_batch_input(self, i):
+        return self.d
+
+
+@pytest.mark.parametrize("case", ["pav_k8_t0.5", "shaped_k8_t0.2"])
+def test_inference_adapter_matches_reference(case):
+    from adanerf_b200.adapter import B200Inference
+    from oracle import adanerf_oracle as orc
+    g = load_golden(case)
+    m = g["meta"]
+    sd0, sd1 = case_weights(case)
+    inf = B200Inference(m["scene_params"], sd0, sd1, m["thr"], m["K"])
+    batch = _Batch({"ImagePose": torch.from_numpy(g["pose"]).reshape(1, 3).cuda(),
+                    "ImageRotation": torch.from_numpy(g["rot"]).reshape(1, 3, 3).cuda(),
+                    "RayDirectionsSamples": torch.from_numpy(g["dirs"]).reshape(1, -1, 3).cuda()})
+    outs, dicts = inf.inference(batch, gradient=False, is_inference=True)
+    rgb = outs[-1][:, :3].cpu().numpy()
+    np.testing.assert_array_equal(dicts[-1]["AdaptiveSamplePositions"].cpu().numpy(), g["asp"])
+    assert orc.psnr(rgb, g["rgb"]) > 45.0
+    assert torch.equal(dicts[-1]["PostProcessedNetworkOutput"], outs[-1])
+    with pytest.raises(NotImplementedError):
+        inf.inference(batch, gradient=True)
+
+
+def test_inference_adapter_dense_returns_oracle_weights():
+    from adanerf_b200.adapter import B200Inference
+    g = load_golden("rand_dense_k128")
+    m = g["meta"]
+    sd0, sd1 = case_weights("rand_dense_k128")
+    inf = B200Inference(m["scene_params"], sd0, sd1, 0.0, 128)
+    batch = _Batch({"ImagePose": torch.from_numpy(g["pose"]).reshape(1, 3), "ImageRotation": torch.from_numpy(g["rot"]).reshape(1, 3, 3),
+                    "RayDirectionsSamples": torch.from_numpy(g["dirs"]).reshape(1, -1, 3)})
+    outs, dicts = inf.inference(batch, gradient=False, is_inference=True)
+    ow = dicts[1]["OracleWeights"].cpu().numpy()
+    np.testing.assert_allclose(ow, g["raw0"], rtol=0, atol=2e-4 * np.abs(g["raw0"]).max())
+    assert "AdaptiveSamplePositions" not in dicts[1]
