@@ -44,7 +44,7 @@ def test_viewer_renders_export_dir(viewer, tmp_path):
     d = _export(tmp_path)
     r = subprocess.run([viewer, d, "-s", "400", "300", "-f", "5", "-w"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
-    m = re.search(r"5 frames 400x300: ([0-9.]+) ms/frame .* ([0-9.]+) per ray", r.stdout)
+    m = re.search(r"5 frames 400x300: ([0-9.]+) ms/frame .*\(([0-9.]+) per ray", r.stdout)
     assert m, r.stdout
     assert 1.0 <= float(m.group(2)) <= 8.0
     ppm = open(os.path.join(d, "adn_frame.ppm"), "rb").read()
