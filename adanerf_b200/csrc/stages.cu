@@ -21,18 +21,30 @@ __device__ __forceinline__ uint32_t bf16x2(float a, float b) {
 
 // enc_L(v) = [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(L-1) v), cos(2^(L-1) v)], each term a 3-vector
 // (src/util/feature_encoding.py:60-73).  Writes 3 + 6L floats.
+// The frequencies are powers of two, so sin / cos of 2^f v follow from those of 2^(f-1) v by the double-angle
+// identities (3 FMA-class ops instead of a ~40-instruction sincosf).  The rounding error doubles per step, so
+// an accurate sincosf re-anchors the recurrence every kAnchor octaves: the result stays within 2^(kAnchor-1)
+// ulp-class (<= ~2e-6 abs) of the directly evaluated value -- far inside the 2^f argument-rounding amplification
+// that the reference's own fp32 evaluation carries (5e-4 at 2^9).
+constexpr int kAnchor = 5;
 template <int L>
 __device__ __forceinline__ void posenc3(const float (&v)[3], float* out) {
   out[0] = v[0];
   out[1] = v[1];
   out[2] = v[2];
 #pragma unroll
-  for (int f = 0; f < L; ++f) {
-    const float freq = float(1 << f);
+  for (int a = 0; a < 3; ++a) {
+    float s = 0.f, c = 1.f;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      float s, c;
-      sincosf(__fmul_rn(v[a], freq), &s, &c);
+    for (int f = 0; f < L; ++f) {
+      if (f % kAnchor == 0) {
+        sincosf(__fmul_rn(v[a], float(1 << f)), &s, &c);
+      } else {
+        const float s2 = 2.0f * s * c;
+        const float c2 = fmaf(-2.0f * s, s, 1.0f);
+        s = s2;
+        c = c2;
+      }
       out[3 + 6 * f + a] = s;
       out[3 + 6 * f + 3 + a] = c;
     }
@@ -75,9 +87,7 @@ __global__ void __launch_bounds__(128)
 stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseDev pd, const float* __restrict__ dirs,
               const __grid_constant__ CameraRays cam, long long n_rays, float* __restrict__ x0, float* __restrict__ ray_o,
               float* __restrict__ ray_d, uint8_t* __restrict__ tiles0) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long n_pad = ((n_rays + kTileM - 1) / kTileM) * kTileM;
-  if (i >= n_pad) return;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // grid covers whole 128-ray tiles
   float f[128];
 #pragma unroll
   for (int j = 0; j < 128; ++j) f[j] = 0.0f;
@@ -125,10 +135,12 @@ stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseD
     }
   }
   if (tiles0) {
-    // packed MLP0 input: per tile [hi blk0 | hi blk1 | lo blk0 | lo blk1], 16 KB each
+    // packed MLP0 input: per tile [hi blk0 | hi blk1 | lo blk0 | lo blk1], 16 KB each.  The block (= one
+    // 128-ray tile) assembles the 64 KB image in shared memory and one thread hands it to the TMA engine
+    // (bulk shared -> global copy): no strided 16-byte global stores.
+    extern __shared__ __align__(1024) uint8_t s_tile[];
     const long long t = i >> 7;
     const uint32_t r = uint32_t(i & 127);
-    uint8_t* tb = tiles0 + size_t(t) * (4 * kBlkBytes);
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
 #pragma unroll
@@ -140,7 +152,6 @@ stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseD
         hi.z = bf16x2(v[4], v[5]);
         hi.w = bf16x2(v[6], v[7]);
         const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
-        uint4 lo;
         uint32_t lw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -148,11 +159,17 @@ stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseD
           const float l1 = v[2 * e + 1] - __uint_as_float(hw[e] & 0xFFFF0000u);
           lw[e] = bf16x2(l0, l1);
         }
-        lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         const uint32_t off = sw128_offset(r, uint32_t(ch * 8));
-        *reinterpret_cast<uint4*>(tb + b * kBlkBytes + off) = hi;
-        *reinterpret_cast<uint4*>(tb + (2 + b) * kBlkBytes + off) = lo;
+        *reinterpret_cast<uint4*>(s_tile + b * kBlkBytes + off) = hi;
+        *reinterpret_cast<uint4*>(s_tile + (2 + b) * kBlkBytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(tiles0 + size_t(t) * (4 * kBlkBytes), s_tile, 4 * kBlkBytes);
+      bulk_commit();
+      bulk_wait_all();
     }
   }
 }
@@ -164,11 +181,18 @@ cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_
   const long long n_pad = ((n_rays + kTileM - 1) / kTileM) * kTileM;
   const unsigned grid = unsigned((n_pad + 127) / 128);
   CameraRays c{};
+  const size_t smem = d_tiles0 ? size_t(4 * kBlkBytes) : 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(stage0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kBlkBytes);
+    cudaFuncSetAttribute(stage0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kBlkBytes);
+    attr = true;
+  }
   if (cam) {
     c = *cam;
-    stage0_kernel<true><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
+    stage0_kernel<true><<<grid, 128, smem, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
   } else {
-    stage0_kernel<false><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
+    stage0_kernel<false><<<grid, 128, smem, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
   }
   return cudaGetLastError();
 }
@@ -464,10 +488,13 @@ stage3_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ ray
       }
     }
     if (tiles1) {
-      // packed MLP1 input: per tile [P: 63 pos features + 0 | V: 27 dir features + zeros], 16 KB each
+      // packed MLP1 input: per tile [P: 63 pos features + 0 | V: 27 dir features + zeros], 16 KB each; staged in
+      // shared memory and written with one bulk shared -> global copy per tile (TMA engine)
+      extern __shared__ __align__(1024) uint8_t s_tile[];
       const long long t = i >> 7;
       const uint32_t r = uint32_t(i & 127);
-      uint8_t* tb = tiles1 + size_t(t) * (2 * kBlkBytes);
+      if (threadIdx.x == 0) bulk_wait_read_all();   // the previous tile's copy has finished reading s_tile
+      __syncthreads();
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
 #pragma unroll
@@ -478,11 +505,18 @@ stage3_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ ray
           hi.y = bf16x2(v[2], v[3]);
           hi.z = bf16x2(v[4], v[5]);
           hi.w = bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(tb + b * kBlkBytes + sw128_offset(r, uint32_t(ch * 8))) = hi;
+          *reinterpret_cast<uint4*>(s_tile + b * kBlkBytes + sw128_offset(r, uint32_t(ch * 8))) = hi;
         }
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        bulk_s2g(tiles1 + size_t(t) * (2 * kBlkBytes), s_tile, 2 * kBlkBytes);
+        bulk_commit();
       }
     }
   }
+  if (tiles1 && threadIdx.x == 0) bulk_wait_all();
 }
 
 cudaError_t launch_stage3(const SceneDev& sc, const float* d_ray_o, const float* d_ray_d, const int32_t* d_ray,
@@ -493,8 +527,13 @@ cudaError_t launch_stage3(const SceneDev& sc, const float* d_ray_o, const float*
   long long blocks = (n_samples + kTileM - 1) / kTileM;
   const long long cap = 148ll * 64;
   if (d_total && blocks > cap) blocks = cap;   // grid-stride when the true count lives on the device
-  stage3_kernel<<<unsigned(blocks), 128, 0, s>>>(sc, d_ray_o, d_ray_d, d_ray, d_z, d_zlut_dense, K, n_samples, d_total, d_x1,
-                                                 d_tiles1);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(stage3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBlkBytes);
+    attr = true;
+  }
+  stage3_kernel<<<unsigned(blocks), 128, d_tiles1 ? size_t(2 * kBlkBytes) : 0, s>>>(sc, d_ray_o, d_ray_d, d_ray, d_z, d_zlut_dense, K,
+                                                                                      n_samples, d_total, d_x1, d_tiles1);
   return cudaGetLastError();
 }
 
