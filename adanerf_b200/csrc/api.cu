@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -50,6 +51,7 @@ struct adn_ctx {
   int dense_K = 0;
   Net net[2];
   int mlp0_terms = 3;
+  int cta_group = 2;              // MLP kernels: 2 = CTA pairs (cta_group::2 MMAs), 1 = single CTA
   int64_t chunk_rays = 0;
   bool profile = false;
   // scratch
@@ -181,7 +183,7 @@ adn_status build_net0(adn_ctx* ctx) {
   if (D < 1 || D > kMaxLayers) return fail(ctx, ADN_ERR_INVALID, "sampling net: need layers.0.weight .. (1-12 layers)");
   const int nsplit = ctx->mlp0_terms == 3 ? 2 : 1;
   net.nsplit = nsplit;
-  net.ng = 1;
+  net.ng = (nsplit == 2) ? 1 : 2;
   MlpProgram P{};
   P.n_layers = D;
   std::vector<uint8_t> wblob;
@@ -416,7 +418,7 @@ int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
 adn_status run_mlp(adn_ctx* ctx, int id, const uint8_t* tiles, float* out, const long long* rows_dev, long long rows,
                    cudaStream_t st) {
   Net& n = ctx->net[id];
-  cudaError_t e = launch_mlp(n.nsplit, n.ng, n.prog, n.d_wblob, tiles, out, rows_dev, rows, ctx->d_err, ctx->num_sms, st,
+  cudaError_t e = launch_mlp(n.nsplit, n.ng, ctx->cta_group, n.prog, n.d_wblob, tiles, out, rows_dev, rows, ctx->d_err, ctx->num_sms, st,
                              ctx->trace_net == id ? ctx->d_trace : nullptr);
   if (e != cudaSuccess) return cuda_fail(ctx, e, id == 0 ? "launch sampling MLP" : "launch shading MLP");
   ctx->stats.kernel_launches++;
@@ -566,6 +568,7 @@ adn_status adn_create(adn_ctx** out, const adn_scene* scene, int device) {
   adn_ctx* ctx = new adn_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char* cg = std::getenv("ADN_CTA_GROUP")) ctx->cta_group = (cg[0] == '1') ? 1 : 2;   // A/B experiments
   ctx->scene = *scene;
   if (cudaSetDevice(device) != cudaSuccess) {
     delete ctx;
@@ -665,6 +668,11 @@ adn_status adn_set_option(adn_ctx* ctx, const char* name, int64_t value) {
     ctx->trace_net = int(value);
     if (value >= 0 && !ctx->d_trace) ADN_CUDA(ctx, cudaMalloc(&ctx->d_trace, sizeof(long long) * 65536));
     if (ctx->d_trace) ADN_CUDA(ctx, cudaMemset(ctx->d_trace, 0, sizeof(long long) * 65536));
+    return ADN_OK;
+  }
+  if (n == "cta_group") {   // experiments / A-B runs: 1 = single-CTA MMAs, 2 = CTA pairs (default)
+    if (value != 1 && value != 2) return fail(ctx, ADN_ERR_INVALID, "cta_group must be 1 or 2");
+    ctx->cta_group = int(value);
     return ADN_OK;
   }
   if (n == "mlp0_terms") {

@@ -10,22 +10,7 @@ namespace adn {
 template <int NSPLIT>
 struct MlpCfg {
   static constexpr int kNB = (NSPLIT == 2) ? 4 : 5;            // activation blocks per slot and term
-  // weight ring: split precision: 3 stages of [128 x 64] hi + lo (one stage per K block and N half);
-  // plain bf16: 2 stages of [256 x 64] (one stage per K block: both N halves, one barrier round trip per 4 MMAs)
-  static constexpr int kStages = (NSPLIT == 2) ? 3 : 2;
-  static constexpr int kStageBytes = 2 * kBlkBytes;
 };
-
-template <int NSPLIT, int NG>
-constexpr size_t mlp_smem_layout_bytes() {
-  return size_t(NG) * NSPLIT * MlpCfg<NSPLIT>::kNB * kBlkBytes + size_t(MlpCfg<NSPLIT>::kStages) * MlpCfg<NSPLIT>::kStageBytes +
-         256 /*barriers*/ + 1024 /*alignment slack*/;
-}
-
-size_t mlp_smem_bytes(int nsplit, int ng) {
-  if (nsplit == 2) return mlp_smem_layout_bytes<2, 1>();
-  return ng == 2 ? mlp_smem_layout_bytes<1, 2>() : mlp_smem_layout_bytes<1, 1>();
-}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -71,15 +56,18 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, c
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
   if (KIND == EK_ACT_RELU_ALPHA) {
+    // four independent partial sums: a single accumulator would be a 32-deep dependent FMA chain
     const float4* w4 = reinterpret_cast<const float4*>(prog.side) + ((prog.alpha_w_off + c) >> 2);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 w = w4[j];
-      alpha = fmaf(v[4 * j + 0], w.x, alpha);
-      alpha = fmaf(v[4 * j + 1], w.y, alpha);
-      alpha = fmaf(v[4 * j + 2], w.z, alpha);
-      alpha = fmaf(v[4 * j + 3], w.w, alpha);
+      a0 = fmaf(v[4 * j + 0], w.x, a0);
+      a1 = fmaf(v[4 * j + 1], w.y, a1);
+      a2 = fmaf(v[4 * j + 2], w.z, a2);
+      a3 = fmaf(v[4 * j + 3], w.w, a3);
     }
+    alpha += (a0 + a1) + (a2 + a3);
   }
   if (kAct) {
     // columns [c, c+32) -> block out_blk0 + c/64, 16-byte chunks (c%64)/8 .. +3, XOR-swizzled by row%8
@@ -130,16 +118,16 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, c
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float4* w4 = reinterpret_cast<const float4*>(prog.side) + ((prog.rgb_w_off + k * 128 + c) >> 2);
-      float acc = rgb[k];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 w = w4[j];
-        acc = fmaf(v[4 * j + 0], w.x, acc);
-        acc = fmaf(v[4 * j + 1], w.y, acc);
-        acc = fmaf(v[4 * j + 2], w.z, acc);
-        acc = fmaf(v[4 * j + 3], w.w, acc);
+        a0 = fmaf(v[4 * j + 0], w.x, a0);
+        a1 = fmaf(v[4 * j + 1], w.y, a1);
+        a2 = fmaf(v[4 * j + 2], w.z, a2);
+        a3 = fmaf(v[4 * j + 3], w.w, a3);
       }
-      rgb[k] = acc;
+      rgb[k] += (a0 + a1) + (a2 + a3);
     }
   }
 }
@@ -158,15 +146,33 @@ __device__ __forceinline__ void epilogue_layer(uint32_t taddr, int c0, int span,
   }
 }
 
-template <int NSPLIT, int NG>
+// Ring geometry.  CG = 1: plain bf16 -> 2 stages of [256 x 64] (one K block, both N halves); split precision -> 3 stages
+// of [128 x 64] hi + lo.  CG = 2 (CTA pair, cta_group::2 MMAs with M = 256): every CTA streams only ITS half of the
+// B rows of each stage, so the same 64 / 96 KB hold twice as many stages (4 / 6): three or more weight stages are in
+// flight while one is consumed, and each SM pulls half the weight bytes from L2.
+template <int NSPLIT, int CG>
+struct RingCfg {
+  static constexpr int kStageBytes = 2 * kBlkBytes / CG;
+  static constexpr int kStages = ((NSPLIT == 2) ? 3 : 2) * CG;
+};
+
+template <int NSPLIT, int NG, int CG>
+constexpr size_t mlp_smem_layout_bytes() {
+  return size_t(NG) * NSPLIT * MlpCfg<NSPLIT>::kNB * kBlkBytes + size_t(RingCfg<NSPLIT, CG>::kStages) * RingCfg<NSPLIT, CG>::kStageBytes +
+         512 /*barriers*/ + 1024 /*alignment slack*/;
+}
+
+template <int NSPLIT, int NG, int CG>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict__ wblob,
                 const uint8_t* __restrict__ in_tiles, float* __restrict__ out,
                 const long long* __restrict__ rows_dev, long long rows_host, int* err_flag, long long* trace) {
   using Cfg = MlpCfg<NSPLIT>;
+  using Ring = RingCfg<NSPLIT, CG>;
   constexpr int NB = Cfg::kNB;
-  constexpr int STAGES = Cfg::kStages;
-  constexpr int STAGE_BYTES = Cfg::kStageBytes;
+  constexpr int STAGES = Ring::kStages;
+  constexpr int STAGE_BYTES = Ring::kStageBytes;
+  constexpr int HALF = kBlkBytes / CG;   // bytes of one [128 x 64] B tile held by one CTA
   constexpr int EW = 16 / NG;   // epilogue warps per tile slot
   constexpr int QW = EW / 4;    // warps sharing one TMEM lane quarter (they split the columns)
   constexpr int CW = 128 / QW;  // accumulator columns per warp and N half
@@ -178,17 +184,24 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   uint8_t* act = smem;                                                   // [NG][NSPLIT][NB] blocks
   uint8_t* ring = act + size_t(NG) * NSPLIT * NB * kBlkBytes;            // [STAGES] stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(STAGES) * STAGE_BYTES);
-  uint64_t* w_full = bars;                 // [STAGES]
-  uint64_t* w_empty = bars + STAGES;       // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;  // [NG]  all MMAs of the layer have retired
-  uint64_t* act_ready = acc_full + NG;     // [NG]  epilogue done: TMEM free, next layer's A operand written
-  uint64_t* in_full = act_ready + NG;      // [NG]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + NG);
+  uint64_t* w_full = bars;                     // [STAGES] this CTA's share of the stage has landed
+  uint64_t* w_empty = w_full + STAGES;         // [STAGES] the MMAs reading the stage have retired (both CTAs)
+  uint64_t* peer_full = w_empty + STAGES;      // [STAGES] leader only: the peer CTA's share has landed
+  uint64_t* acc_full = peer_full + STAGES;     // [NG]  all MMAs of the layer have retired
+  uint64_t* act_ready = acc_full + NG;         // [NG]  this CTA's epilogue warps are done (TMEM free, A operand written)
+  uint64_t* peer_act = act_ready + NG;         // [NG]  leader only: the peer's act_ready, forwarded by its helper warp
+  uint64_t* in_full = peer_act + NG;           // [NG]  this CTA's tile input has landed
+  uint64_t* peer_in = in_full + NG;            // [NG]  leader only: the peer's tile input has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_in + NG);
 
   // warp index through a lane-0 broadcast: tells the compiler it is warp uniform, so the role branches
   // (and everything indexed by loop counters inside them) stay on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  const long long n_units = gridDim.x / CG;   // persistent work units: CTAs or CTA pairs
+  const long long unit = blockIdx.x / CG;
 
   const long long rows = rows_dev ? *rows_dev : rows_host;
   const long long n_tiles = (rows + kTileM - 1) / kTileM;
@@ -197,29 +210,28 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
+      mbar_init(&peer_full[s], 1);
     }
     for (int g = 0; g < NG; ++g) {
       mbar_init(&acc_full[g], 1);
       mbar_init(&act_ready[g], EW);
+      mbar_init(&peer_act[g], 1);
       mbar_init(&in_full[g], 1);
+      mbar_init(&peer_in[g], 1);
     }
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
+  if (warp == kMmaWarp) tmem_alloc_cg<CG>(tmem_slot, 512);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   auto act_ptr = [&](int g, int term, int blk) -> uint8_t* {
     return act + (size_t(g * NSPLIT + term) * NB + blk) * kBlkBytes;
   };
-  auto tile_of = [&](long long iter, int g) -> long long {
-    return (iter * gridDim.x + blockIdx.x) * NG + g;
-  };
+  // first tile of the unit's tile group for (iter, slot); CTA `cta_rank` of a pair owns tile first + cta_rank
+  auto first_tile = [&](long long iter, int g) -> long long { return ((iter * n_units + unit) * NG + g) * CG; };
   // Optional timeline (debug): a few warps of CTA 0 record (clock, code) pairs into private regions of `trace`
   // (region r: words [r*8192, (r+1)*8192), word 0 = count); code = slot<<16 | layer<<8 | event.  Off (nullptr)
   // in normal operation.
@@ -236,24 +248,44 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
 
   if (warp == kProducerWarp) {
     // ===================================================================== weight producer
+    // Streams this CTA's share of every weight stage: stage i of a layer is [n_half x 128 rows x 64] (plain bf16)
+    // or [128 rows x 64] hi + lo (split); with CG = 2 each CTA takes rows [rank*64, +64) of every 128-row tile.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long iter = 0;; ++iter) {
-        if (tile_of(iter, 0) >= n_tiles) break;
+        if (first_tile(iter, 0) >= n_tiles) break;
         for (int l = 0; l < prog.n_layers; ++l) {
           const MlpLayer& L = prog.layers[l];
-          // split precision: one stage per (K block, N half) = hi + lo tiles; plain bf16: one stage per K block
-          // holding the layer's 1 or 2 N halves back to back
           const int n_st = (NSPLIT == 2) ? int(L.n_kb) * int(L.n_half) : int(L.n_kb);
-          const uint32_t st_bytes = (NSPLIT == 2) ? uint32_t(STAGE_BYTES) : uint32_t(L.n_half) * kBlkBytes;
+          const uint32_t src_stride = (NSPLIT == 2) ? uint32_t(2 * kBlkBytes) : uint32_t(L.n_half) * kBlkBytes;
           for (int g = 0; g < NG; ++g) {
-            if (tile_of(iter, g) >= n_tiles) continue;
+            if (first_tile(iter, g) >= n_tiles) continue;
             const uint8_t* src = wblob + L.w_off;
             for (int i = 0; i < n_st; ++i) {
+              if (l == 2) tr(5, g, stage, 8);
               mbar_wait(&w_empty[stage], phase ^ 1, err_flag, 1);
-              mbar_arrive_expect_tx(&w_full[stage], st_bytes);
-              bulk_g2s(ring + size_t(stage) * STAGE_BYTES, src + size_t(i) * st_bytes, st_bytes, &w_full[stage]);
+              if (l == 2) tr(5, g, stage, 9);
+              uint8_t* dst = ring + size_t(stage) * STAGE_BYTES;
+              const uint8_t* s0 = src + size_t(i) * src_stride;
+              if (NSPLIT == 2) {
+                // [hi 128 rows | lo 128 rows] -> this CTA's row range of each
+                mbar_arrive_expect_tx(&w_full[stage], 2 * HALF);
+                bulk_g2s(dst, s0 + cta_rank * HALF, HALF, &w_full[stage]);
+                bulk_g2s(dst + HALF, s0 + kBlkBytes + cta_rank * HALF, HALF, &w_full[stage]);
+              } else if (L.n_half == 2) {
+                if (CG == 2) {
+                  // N = 256 over the pair: CTA r holds B rows [128 r, 128 r + 128) = N half r
+                  mbar_arrive_expect_tx(&w_full[stage], kBlkBytes);
+                  bulk_g2s(dst, s0 + cta_rank * kBlkBytes, kBlkBytes, &w_full[stage]);
+                } else {
+                  mbar_arrive_expect_tx(&w_full[stage], 2 * kBlkBytes);
+                  bulk_g2s(dst, s0, 2 * kBlkBytes, &w_full[stage]);
+                }
+              } else {
+                mbar_arrive_expect_tx(&w_full[stage], HALF);
+                bulk_g2s(dst, s0 + cta_rank * HALF, HALF, &w_full[stage]);
+              }
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -267,31 +299,46 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     // =================================================================== barrier helper
     // Walks the same schedule as the MMA issuer one step ahead and turns every mbarrier round trip
     // (try_wait is ~100-200 cycles even when the phase has already completed) into a named-barrier
-    // arrival, which the issuer consumes with a ~tens-of-cycles bar.sync: the issuer's serial chain per
-    // K block shrinks to "bar.sync, issue 4 MMAs, commit".
+    // arrival, which the issuer consumes with a ~tens-of-cycles bar.sync.  In a CTA pair the peer's helper
+    // forwards "my share has landed" to the leader with remote mbarrier arrivals.
     int stage = 0;
     uint32_t phase = 0;
     uint32_t in_phase[NG], ar_phase[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) in_phase[g] = ar_phase[g] = 0;
     for (long long iter = 0;; ++iter) {
-      if (tile_of(iter, 0) >= n_tiles) break;
+      if (first_tile(iter, 0) >= n_tiles) break;
       for (int l = 0; l < prog.n_layers; ++l) {
         const MlpLayer& L = prog.layers[l];
         const int n_st = (NSPLIT == 2) ? int(L.n_kb) * int(L.n_half) : int(L.n_kb);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-          if (tile_of(iter, g) >= n_tiles) continue;
+          if (first_tile(iter, g) >= n_tiles) continue;
           if (l == 0 || (L.flags & LF_WAIT_IN)) {
             mbar_wait(&in_full[g], in_phase[g], err_flag, 2);
+            if (CG == 2) {
+              if (leader) mbar_wait(&peer_in[g], in_phase[g], err_flag, 7);
+              else if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&peer_in[g]), 0));
+            }
             in_phase[g] ^= 1;
           }
           mbar_wait(&act_ready[g], ar_phase[g], err_flag, 3);
+          if (CG == 2) {
+            if (leader) mbar_wait(&peer_act[g], ar_phase[g], err_flag, 9);
+            else if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&peer_act[g]), 0));
+          }
           ar_phase[g] ^= 1;
-          named_bar_arrive(kBarSlot + g, 64);
+          if (leader) named_bar_arrive(kBarSlot + g, 64);
           for (int i = 0; i < n_st; ++i) {
+            if (lane == 0 && l == 2) tr(6, g, stage, 10);
             mbar_wait(&w_full[stage], phase, err_flag, 4);
-            named_bar_arrive(kBarStage + stage, 64);
+            if (lane == 0 && l == 2) tr(6, g, stage, 11);
+            if (CG == 2) {
+              if (leader) mbar_wait(&peer_full[stage], phase, err_flag, 8);
+              else if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&peer_full[stage]), 0));
+              if (lane == 0 && l == 2) tr(6, g, stage, 12);
+            }
+            if (leader) named_bar_arrive(kBarStage + stage, 64);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -301,87 +348,89 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       }
     }
   } else if (warp == kMmaWarp) {
-    // ========================================================================== MMA issuer
+    // ========================================================================== MMA issuer (leader CTA only)
     // The whole warp walks the schedule converged (every quantity below is warp uniform, so the
     // descriptors live in uniform registers); one elected lane issues the tcgen05 instructions.
-    // With plain bf16 (NSPLIT == 1) a 256-wide layer is issued as N = 256 MMAs whose B operand spans the two
-    // adjacent ring stages (kb, half 0) and (kb, half 1): half the instructions per flop of N = 128.
-    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128);
-    constexpr uint32_t idesc256 = make_idesc_bf16(128, 256);
-    int stage = 0;
-    const uint64_t desc_hi = make_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // constant upper word
-    const uint32_t desc_lo_const = uint32_t(make_desc_sw128(0) & 0xFFFF0000ull);
-    // low descriptor word of an address: a K step of 16 elements (+32 B) is "+2" on this word
-    auto lo_of = [&](uint32_t addr) -> uint32_t { return desc_lo_const | (addr >> 4); };
-    const uint32_t ring_lo = lo_of(smem_u32(ring));
-    const uint32_t act_lo0 = lo_of(smem_u32(act));
-    auto desc = [&](uint32_t lo) -> uint64_t { return desc_hi | uint64_t(lo); };
-    for (long long iter = 0;; ++iter) {
-      if (tile_of(iter, 0) >= n_tiles) break;
-      for (int l = 0; l < prog.n_layers; ++l) {
-        const MlpLayer& L = prog.layers[l];
-        const bool wide = (NSPLIT == 1) && (L.n_half == 2);
-        // this layer's A block indices packed 4 bits each: the issue loop extracts them with a shift instead
-        // of a dependent constant-bank load per K block
-        uint32_t blks = 0;
+    // Plain bf16: a 256-wide layer is issued as N = 256 MMAs (one stage = one K block).  CG = 2: M = 256 across the
+    // CTA pair -- A rows and B rows of both CTAs are addressed by the same shared-memory offsets.
+    if (leader) {
+      constexpr uint32_t idesc128 = make_idesc_bf16(128 * CG, 128);
+      constexpr uint32_t idesc256 = make_idesc_bf16(128 * CG, 256);
+      int stage = 0;
+      const uint64_t desc_hi = make_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // constant upper word
+      const uint32_t desc_lo_const = uint32_t(make_desc_sw128(0) & 0xFFFF0000ull);
+      // low descriptor word of an address: a K step of 16 elements (+32 B) is "+2" on this word
+      auto lo_of = [&](uint32_t addr) -> uint32_t { return desc_lo_const | (addr >> 4); };
+      const uint32_t ring_lo = lo_of(smem_u32(ring));
+      const uint32_t act_lo0 = lo_of(smem_u32(act));
+      auto desc = [&](uint32_t lo) -> uint64_t { return desc_hi | uint64_t(lo); };
+      for (long long iter = 0;; ++iter) {
+        if (first_tile(iter, 0) >= n_tiles) break;
+        for (int l = 0; l < prog.n_layers; ++l) {
+          const MlpLayer& L = prog.layers[l];
+          const bool wide = (NSPLIT == 1) && (L.n_half == 2);
+          // this layer's A block indices packed 4 bits each: the issue loop extracts them with a shift instead
+          // of a dependent constant-bank load per K block
+          uint32_t blks = 0;
 #pragma unroll
-        for (int kb = 0; kb < 6; ++kb) blks |= uint32_t(L.a_blk[kb] & 15) << (4 * kb);
+          for (int kb = 0; kb < 6; ++kb) blks |= uint32_t(L.a_blk[kb] & 15) << (4 * kb);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if (tile_of(iter, g) >= n_tiles) continue;
-          if (lane == 0) tr(0, g, l, 0);
-          named_bar_sync(kBarSlot + g, 64);   // helper has seen in_full / act_ready of this slot
-          tc_fence_after();
-          if (lane == 0) tr(0, g, l, 1);
-          const uint32_t d0 = tmem_base + uint32_t(g * 256);
-          for (int kb = 0; kb < L.n_kb; ++kb) {
-            const uint32_t a_hi = act_lo0 + (uint32_t(g * NSPLIT * NB) + ((blks >> (4 * kb)) & 15u)) * (kBlkBytes >> 4);
-            const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * (kBlkBytes >> 4);
-            if (NSPLIT == 1) {
-              if (lane == 0 && l == 2) tr(0, g, kb, 5);
-              named_bar_sync(kBarStage + stage, 64);   // helper has seen w_full[stage]
-              tc_fence_after();
-              if (lane == 0 && l == 2) tr(0, g, kb, 6);
-              const uint32_t b = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
-              if (elect_one()) {
-                if (wide) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc256, (kb > 0 || k > 0) ? 1u : 0u);
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&w_empty[stage]);
-              }
-              __syncwarp();
-              if (lane == 0 && l == 2) tr(0, g, kb, 7);
-              stage ^= 1;
-            } else {
-              for (int nh = 0; nh < L.n_half; ++nh) {
-                named_bar_sync(kBarStage + stage, 64);
+          for (int g = 0; g < NG; ++g) {
+            if (first_tile(iter, g) >= n_tiles) continue;
+            if (lane == 0) tr(0, g, l, 0);
+            named_bar_sync(kBarSlot + g, 64);   // helper has seen in_full / act_ready of this slot
+            tc_fence_after();
+            if (lane == 0) tr(0, g, l, 1);
+            const uint32_t d0 = tmem_base + uint32_t(g * 256);
+            for (int kb = 0; kb < L.n_kb; ++kb) {
+              const uint32_t a_hi = act_lo0 + (uint32_t(g * NSPLIT * NB) + ((blks >> (4 * kb)) & 15u)) * (kBlkBytes >> 4);
+              const uint32_t a_lo = a_hi + uint32_t((NSPLIT - 1) * NB) * (kBlkBytes >> 4);
+              if (NSPLIT == 1) {
+                if (lane == 0 && l == 2) tr(0, g, kb, 5);
+                named_bar_sync(kBarStage + stage, 64);   // helper has seen w_full[stage] (of both CTAs)
                 tc_fence_after();
-                const uint32_t b_hi = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
-                const uint32_t b_lo = b_hi + (kBlkBytes >> 4);
-                const uint32_t d = d0 + uint32_t(nh * 128);
+                if (lane == 0 && l == 2) tr(0, g, kb, 6);
+                const uint32_t b = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
                 if (elect_one()) {
+                  if (wide) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    umma_bf16(d, desc(a_hi + 2 * k), desc(b_hi + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_bf16(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
-                    umma_bf16(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
+                    for (int k = 0; k < 4; ++k)
+                      umma_bf16_cg<CG>(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc256, (kb > 0 || k > 0) ? 1u : 0u);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_bf16_cg<CG>(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
                   }
-                  umma_commit(&w_empty[stage]);
+                  umma_commit_cg<CG>(&w_empty[stage]);
                 }
                 __syncwarp();
+                if (lane == 0 && l == 2) tr(0, g, kb, 7);
                 if (++stage == STAGES) stage = 0;
+              } else {
+                for (int nh = 0; nh < L.n_half; ++nh) {
+                  named_bar_sync(kBarStage + stage, 64);
+                  tc_fence_after();
+                  const uint32_t b_hi = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
+                  const uint32_t b_lo = b_hi + (HALF >> 4);
+                  const uint32_t d = d0 + uint32_t(nh * 128);
+                  if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_hi + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
+                      umma_bf16_cg<CG>(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
+                      umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
+                    }
+                    umma_commit_cg<CG>(&w_empty[stage]);
+                  }
+                  __syncwarp();
+                  if (++stage == STAGES) stage = 0;
+                }
               }
             }
+            if (elect_one()) umma_commit_cg<CG>(&acc_full[g]);
+            __syncwarp();
+            if (lane == 0) tr(0, g, l, 2);
           }
-          if (elect_one()) umma_commit(&acc_full[g]);
-          __syncwarp();
-          if (lane == 0) tr(0, g, l, 2);
         }
       }
     }
@@ -396,21 +445,29 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     uint32_t acc_phase = 0;
     const uint32_t act_hi = smem_u32(act_ptr(g, 0, 0));
     const uint32_t act_lo = smem_u32(act_ptr(g, NSPLIT - 1, 0));
+    // act_ready is local to every CTA (cheap release.cta arrive); in a CTA pair the peer's helper warp forwards it
+    auto arrive_act_ready = [&]() { mbar_arrive(&act_ready[g]); };
     for (long long iter = 0;; ++iter) {
-      const long long t = tile_of(iter, g);
-      if (t >= n_tiles) break;
+      const long long t0 = first_tile(iter, g);
+      if (t0 >= n_tiles) break;
+      const long long t = t0 + cta_rank;           // may be one past the end in the last pair: rows masked, protocol kept
+      const bool have_tile = t < n_tiles;
       const long long grow = t * kTileM + row_in_tile;
       if (e == 0 && lane == 0) {
-        const uint8_t* src = in_tiles + size_t(t) * prog.in_tile_stride;
-        const uint32_t bytes = uint32_t(prog.in0_nblk) * kBlkBytes;
-        mbar_arrive_expect_tx(&in_full[g], bytes * NSPLIT);
-        bulk_g2s(act_ptr(g, 0, prog.in0_blk), src + prog.in0_off, bytes, &in_full[g]);
-        if (NSPLIT == 2) bulk_g2s(act_ptr(g, 1, prog.in0_blk), src + prog.in0_lo_off, bytes, &in_full[g]);
+        if (have_tile) {
+          const uint8_t* src = in_tiles + size_t(t) * prog.in_tile_stride;
+          const uint32_t bytes = uint32_t(prog.in0_nblk) * kBlkBytes;
+          mbar_arrive_expect_tx(&in_full[g], bytes * NSPLIT);
+          bulk_g2s(act_ptr(g, 0, prog.in0_blk), src + prog.in0_off, bytes, &in_full[g]);
+          if (NSPLIT == 2) bulk_g2s(act_ptr(g, 1, prog.in0_blk), src + prog.in0_lo_off, bytes, &in_full[g]);
+        } else {
+          mbar_arrive(&in_full[g]);
+        }
       }
       // accumulator columns and activation buffers of this slot are free for layer 0
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&act_ready[g]);
+      if (lane == 0) arrive_act_ready();
 
       float alpha = 0.0f;
       float rgb[3] = {0.0f, 0.0f, 0.0f};
@@ -423,9 +480,13 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         tc_fence_after();
         if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 3);
         if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
-          mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
-          bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
-                   &in_full[g]);
+          if (have_tile) {
+            mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
+            bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
+                     &in_full[g]);
+          } else {
+            mbar_arrive(&in_full[g]);
+          }
         }
         for (int h = 0; h < L.n_half; ++h) {
           const int c0 = h * 128 + sub * CW;
@@ -454,7 +515,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
           if (QW > 1) {
             float4* scratch = reinterpret_cast<float4*>(act_ptr(g, 0, prog.hid_blk0));
             if (sub > 0) scratch[(sub - 1) * kTileM + row_in_tile] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(EW * 32) : "memory");
+            named_bar_sync(1 + g, EW * 32);
             if (sub == 0) {
 #pragma unroll
               for (int q = 1; q < QW; ++q) {
@@ -465,7 +526,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
                 alpha += p.w;
               }
             }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(EW * 32) : "memory");
+            named_bar_sync(1 + g, EW * 32);
           }
           if (sub == 0 && grow < rows) {
             const float ab = prog.side[prog.alpha_b_off];
@@ -478,17 +539,17 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         if (l + 1 < prog.n_layers) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&act_ready[g]);
+          if (lane == 0) arrive_act_ready();
         }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody leaves while its partner may still signal it
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_cg<CG>(tmem_base, 512);
   }
 }
 
@@ -540,34 +601,48 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, long long rows_hos
 }
 
 // -------------------------------------------------------------------------------------------------
-template <int NSPLIT, int NG>
+template <int NSPLIT, int NG, int CG>
 static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles,
                                 float* out, const long long* rows_dev, long long rows_host, int* err_flag, int num_sms,
                                 cudaStream_t stream, long long* trace) {
   static bool attr_set = false;
-  const size_t smem = mlp_smem_layout_bytes<NSPLIT, NG>();
+  const size_t smem = mlp_smem_layout_bytes<NSPLIT, NG, CG>();
+  auto kernel = mlp_umma_kernel<NSPLIT, NG, CG>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_umma_kernel<NSPLIT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  int grid = num_sms;
+  int grid = (num_sms / CG) * CG;   // persistent: one CTA (or CTA pair) per SM (pair)
   if (!rows_dev) {
     const long long n_tiles = (rows_host + kTileM - 1) / kTileM;
-    const long long need = (n_tiles + NG - 1) / NG;
-    if (need < grid) grid = int(need < 1 ? 1 : need);
+    const long long need = ((n_tiles + NG * CG - 1) / (NG * CG)) * CG;
+    if (need < grid) grid = int(need < CG ? CG : need);
   }
-  mlp_umma_kernel<NSPLIT, NG><<<grid, kMlpThreads, smem, stream>>>(prog, wblob, in_tiles, out, rows_dev, rows_host,
-                                                                   err_flag, trace);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(kMlpThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, trace);
 }
 
-cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob,
+cudaError_t launch_mlp(int nsplit, int ng, int cg, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host, int* err_flag,
                        int num_sms, cudaStream_t stream, long long* trace) {
-  if (nsplit == 2) return launch_mlp_t<2, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
-  if (ng == 2) return launch_mlp_t<1, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
-  return launch_mlp_t<1, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+  if (cg == 2) {
+    if (nsplit == 2) return launch_mlp_t<2, 1, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+    return launch_mlp_t<1, 2, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+  }
+  if (nsplit == 2) return launch_mlp_t<2, 1, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+  return launch_mlp_t<1, 2, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
 }
 
 cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat, const InputLayout& lay,

@@ -70,10 +70,9 @@ struct InputLayout {
   int32_t nsplit;
 };
 
-size_t mlp_smem_bytes(int nsplit, int ng);
 
 // Launchers (defined in mlp_umma.cu).  rows_dev may be null (then rows_host is used).
-cudaError_t launch_mlp(int nsplit, int ng, const MlpProgram& prog, const uint8_t* wblob,
+cudaError_t launch_mlp(int nsplit, int ng, int cg, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host,
                        int* err_flag, int num_sms, cudaStream_t stream, long long* trace = nullptr);
 cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat,

@@ -24,20 +24,20 @@ buf = np.zeros(65536, dtype=np.int64)
 r.lib.adn_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
 assert r.lib.adn_debug_read_trace(r.handle, buf.ctypes.data, 65536) == 0
 rows = []
-for region in range(5):
+for region in range(7):
     base = buf[region * 8192:(region + 1) * 8192]
     n = int(base[0])
     ev = base[2:2 + 2 * n].reshape(-1, 2)
-    role = 1 if region == 0 else (2 if (region - 1) % 2 == 0 else 3)
+    role = 1 if region == 0 else (5 if region == 5 else (6 if region == 6 else (2 if (region - 1) % 2 == 0 else 3)))
     rows += [(int(t), role, (int(c) >> 16) & 255, (int(c) >> 8) & 255, int(c) & 255) for t, c in ev]
 n = len(rows)
 t0 = min(x[0] for x in rows)
 rows = sorted((x[0] - t0,) + x[1:] for x in rows)
-names = {0: "mma wait", 1: "mma issue", 2: "mma committed", 3: "acc seen", 4: "epi done", 5: "kb: before w_full", 6: "kb: weights ready", 7: "kb: issued"}
+names = {0: "mma wait", 1: "mma issue", 2: "mma committed", 3: "acc seen", 4: "epi done", 5: "kb: before w_full", 6: "kb: weights ready", 7: "kb: issued", 8: "prod: wait empty", 9: "prod: empty seen, copy", 10: "help: wait full", 11: "help: local full", 12: "help: peer full"}
 print("events", n)
 # skip the first 3 tiles of each slot, then print ~2 tiles worth of events
 start = [i for i, x in enumerate(rows) if x[1] == 1 and x[3] == 0 and x[4] == 0][6] if n > 400 else 0
-for x in rows[start:start + 60]:
+for x in rows[start:start + 130]:
     print(f"{x[0]:9d}  role={x[1]} slot={x[2]} layer={x[3]:2d}  {names[x[4]]}")
 # per layer statistics over the whole trace
 import collections
