@@ -62,6 +62,9 @@ struct adn_ctx {
   int trace_net = -1;
   // pinned staging for the *_host entry points
   Buf h_in, h_out, h_ns;
+  // caller buffers page-locked in place (cudaHostRegister) so repeated calls DMA straight from / to them
+  struct Reg { const void* p = nullptr; size_t bytes = 0; const void* last_seen = nullptr; };
+  Reg reg[3];
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev[8] = {};
   adn_stats stats{};
@@ -104,6 +107,34 @@ adn_status ensure_pinned(adn_ctx* ctx, Buf& b, size_t bytes) {
   ADN_CUDA(ctx, cudaMallocHost(&b.p, bytes));
   b.cap = bytes;
   return ADN_OK;
+}
+
+// Page-locks a caller buffer in place (slot: 0 = dirs in, 1 = rgb out, 2 = n_samples out).  Returns false when the
+// driver refuses (e.g. read-only or already-registered memory): the caller then goes through the staging buffer.
+bool pin_in_place(adn_ctx* ctx, int slot, const void* p, size_t bytes) {
+  adn_ctx::Reg& r = ctx->reg[slot];
+  if (r.p == p && r.bytes >= bytes) return true;
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;   // already pinned
+  cudaGetLastError();
+  // cudaHostRegister costs milliseconds: only pay it for a buffer the caller demonstrably reuses (same pointer on
+  // two consecutive calls); one-shot buffers go through the context's pinned staging area.
+  if (r.last_seen != p) {
+    r.last_seen = p;
+    return false;
+  }
+  if (r.p) {
+    cudaHostUnregister(const_cast<void*>(r.p));
+    r.p = nullptr;
+    r.bytes = 0;
+  }
+  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  r.p = p;
+  r.bytes = bytes;
+  return true;
 }
 
 // ---- bf16 helpers (host) -------------------------------------------------------------------
@@ -614,6 +645,8 @@ void adn_destroy(adn_ctx* ctx) {
                  &ctx->rayidx, &ctx->zbuf, &ctx->zpbuf, &ctx->tiles1, &ctx->raw1,  &ctx->s2scratch, &ctx->rgb,   &ctx->rgba, &ctx->x1};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (auto& r : ctx->reg)
+    if (r.p) cudaHostUnregister(const_cast<void*>(r.p));
   Buf* pinned[] = {&ctx->h_in, &ctx->h_out, &ctx->h_ns};
   for (Buf* b : pinned)
     if (b->p) cudaFreeHost(b->p);
@@ -743,9 +776,15 @@ adn_status adn_render_rays_host(adn_ctx* ctx, const float* pose, const float* ro
   if ((s = ensure_pinned(ctx, ctx->h_out, size_t(n_rays) * 12)) != ADN_OK) return s;
   if (h_nsamples && (s = ensure_pinned(ctx, ctx->h_ns, size_t(n_rays) * 4)) != ADN_OK) return s;
   cudaStream_t st = ctx->own_stream;
-  std::memcpy(ctx->h_in.p, h_dirs, size_t(n_rays) * 12);
-  ADN_CUDA(ctx, cudaMemcpyAsync(ctx->dirs.p, ctx->h_in.p, size_t(n_rays) * 12, cudaMemcpyHostToDevice, st));
-
+  const bool in_pinned = pin_in_place(ctx, 0, h_dirs, size_t(n_rays) * 12);
+  const bool out_pinned = pin_in_place(ctx, 1, h_rgb, size_t(n_rays) * 12);
+  const bool ns_pinned = h_nsamples && pin_in_place(ctx, 2, h_nsamples, size_t(n_rays) * 4);
+  const void* src = h_dirs;
+  if (!in_pinned) {
+    std::memcpy(ctx->h_in.p, h_dirs, size_t(n_rays) * 12);
+    src = ctx->h_in.p;
+  }
+  ADN_CUDA(ctx, cudaMemcpyAsync(ctx->dirs.p, src, size_t(n_rays) * 12, cudaMemcpyHostToDevice, st));
   int32_t* d_ns = nullptr;
   if (h_nsamples) {
     if ((s = ensure(ctx, ctx->rgba, size_t(n_rays) * 4)) != ADN_OK) return s;
@@ -754,12 +793,14 @@ adn_status adn_render_rays_host(adn_ctx* ctx, const float* pose, const float* ro
   s = render_impl(ctx, pose, rot, static_cast<float*>(ctx->dirs.p), nullptr, n_rays, thr, K, static_cast<float*>(ctx->rgb.p),
                   nullptr, d_ns, nullptr, st);
   if (s != ADN_OK) return s;
-  ADN_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, ctx->rgb.p, size_t(n_rays) * 12, cudaMemcpyDeviceToHost, st));
-  if (h_nsamples) ADN_CUDA(ctx, cudaMemcpyAsync(ctx->h_ns.p, d_ns, size_t(n_rays) * 4, cudaMemcpyDeviceToHost, st));
+  ADN_CUDA(ctx, cudaMemcpyAsync(out_pinned ? static_cast<void*>(h_rgb) : ctx->h_out.p, ctx->rgb.p, size_t(n_rays) * 12,
+                                cudaMemcpyDeviceToHost, st));
+  if (h_nsamples)
+    ADN_CUDA(ctx, cudaMemcpyAsync(ns_pinned ? static_cast<void*>(h_nsamples) : ctx->h_ns.p, d_ns, size_t(n_rays) * 4,
+                                  cudaMemcpyDeviceToHost, st));
   ADN_CUDA(ctx, cudaStreamSynchronize(st));
-  std::memcpy(h_rgb, ctx->h_out.p, size_t(n_rays) * 12);
-  if (h_nsamples) std::memcpy(h_nsamples, ctx->h_ns.p, size_t(n_rays) * 4);
-
+  if (!out_pinned) std::memcpy(h_rgb, ctx->h_out.p, size_t(n_rays) * 12);
+  if (h_nsamples && !ns_pinned) std::memcpy(h_nsamples, ctx->h_ns.p, size_t(n_rays) * 4);
   return check_device_error(ctx);
 }
 
@@ -779,14 +820,19 @@ adn_status adn_render_camera_host(adn_ctx* ctx, const float* pose, const float* 
     d_ns = static_cast<int32_t*>(ctx->rgba.p);
   }
   cudaStream_t st = ctx->own_stream;
+  const bool out_pinned = pin_in_place(ctx, 1, h_rgb, size_t(n_rays) * 12);
+  const bool ns_pinned = h_nsamples && pin_in_place(ctx, 2, h_nsamples, size_t(n_rays) * 4);
   const CameraRays cam = make_camera(ctx, W, H, row0);
   s = render_impl(ctx, pose, rot, nullptr, &cam, n_rays, thr, K, static_cast<float*>(ctx->rgb.p), nullptr, d_ns, nullptr, st);
   if (s != ADN_OK) return s;
-  ADN_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, ctx->rgb.p, size_t(n_rays) * 12, cudaMemcpyDeviceToHost, st));
-  if (h_nsamples) ADN_CUDA(ctx, cudaMemcpyAsync(ctx->h_ns.p, d_ns, size_t(n_rays) * 4, cudaMemcpyDeviceToHost, st));
+  ADN_CUDA(ctx, cudaMemcpyAsync(out_pinned ? static_cast<void*>(h_rgb) : ctx->h_out.p, ctx->rgb.p, size_t(n_rays) * 12,
+                                cudaMemcpyDeviceToHost, st));
+  if (h_nsamples)
+    ADN_CUDA(ctx, cudaMemcpyAsync(ns_pinned ? static_cast<void*>(h_nsamples) : ctx->h_ns.p, d_ns, size_t(n_rays) * 4,
+                                  cudaMemcpyDeviceToHost, st));
   ADN_CUDA(ctx, cudaStreamSynchronize(st));
-  std::memcpy(h_rgb, ctx->h_out.p, size_t(n_rays) * 12);
-  if (h_nsamples) std::memcpy(h_nsamples, ctx->h_ns.p, size_t(n_rays) * 4);
+  if (!out_pinned) std::memcpy(h_rgb, ctx->h_out.p, size_t(n_rays) * 12);
+  if (h_nsamples && !ns_pinned) std::memcpy(h_nsamples, ctx->h_ns.p, size_t(n_rays) * 4);
   return check_device_error(ctx);
 }
 

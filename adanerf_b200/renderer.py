@@ -151,12 +151,13 @@ class Renderer:
                                                          out.data_ptr(), self._stream()))
         return out
 
-    def render_rays_host(self, pose, rot, dirs_np, thr, K, want_nsamples=True):
-        """Host buffers in, host buffers out (H2D / D2H inside the call)."""
+    def render_rays_host(self, pose, rot, dirs_np, thr, K, want_nsamples=True, out=None):
+        """Host buffers in, host buffers out (H2D / D2H inside the call).  Reusing `dirs_np` / `out` across calls lets
+        the library page-lock them in place and DMA without a staging copy."""
         p, r = self._pose_rot(pose, rot)
         d = np.ascontiguousarray(dirs_np, dtype=np.float32).reshape(-1, 3)
         n = d.shape[0]
-        rgb = np.empty((n, 3), dtype=np.float32)
+        rgb = out if out is not None else np.empty((n, 3), dtype=np.float32)
         ns = np.empty((n,), dtype=np.int32) if want_nsamples else None
         self._check(self.lib.adn_render_rays_host(self.handle, _fptr(p), _fptr(r), d.ctypes.data, n, float(thr), int(K),
                                                   rgb.ctypes.data, ns.ctypes.data if ns is not None else None))

@@ -357,3 +357,26 @@ def test_error_paths(bare):
     with pytest.raises(AdnError):
         r.render_camera(torch.zeros(3), torch.eye(3), 8, 8, 0.2, 0)
     r.close()
+
+
+@pytest.mark.parametrize("K", [8, 16])
+def test_threshold_sweep_vs_oracle(K, pavillon_weights):
+    """BASELINE config 5: thr in {0.05, 0.1, 0.2, 0.3, 0.5} with the trained Pavillon weights (ragged sample counts at
+    the higher thresholds).  Compared with the CPU oracle run on this host: sample counts must agree on >= 99 % of
+    the rays (a borderline logit may flip between two fp32 evaluation orders) and PSNR(ours, oracle) >= 50 dB."""
+    sd0, sd1 = pavillon_weights
+    scene = orc.SCENE_PAVILLON
+    r = _renderer(scene, sd0, sd1)
+    W = H = 800
+    idx = torch.arange(0, W * H, 1237)[:512]
+    dirs = torch.from_numpy(orc.generate_ray_directions(W, H, scene["fov"]).reshape(-1, 3)).float()[idx]
+    pose = torch.tensor(scene["view_cell_center"]) + torch.tensor([0.05, -0.03, 0.02])
+    rot = torch.tensor([[1, 0, 0], [0, 0, -1], [0, 1, 0]], dtype=torch.float32)
+    for thr in (0.05, 0.1, 0.2, 0.3, 0.5):
+        ref = orc.render_rays(pose, rot, dirs, sd0, sd1, scene, thr, K)
+        out = r.render_rays(pose, rot, dirs.cuda(), thr, K)
+        same = (out["n_samples"].cpu().long() == ref["n_samples"]).float().mean().item()
+        p = orc.psnr(out["rgb"].cpu(), ref["rgb"])
+        print(f"K={K} thr={thr}: mean spr {ref['n_samples'].float().mean():.2f}, identical counts {same:.4f}, PSNR {p:.2f} dB")
+        assert same >= 0.99 and p >= 50.0
+    r.close()
