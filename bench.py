@@ -51,6 +51,35 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full summary (None when absent)."""
+    p = os.path.join(ROOT, "profiles", "ncu_r1_summary.json")
+    try:
+        d = json.load(open(p))[kernel]
+        return int(d["dram_rd"] + d["dram_wr"])
+    except Exception:
+        return None
+
+
+def stage_rooflines(stage_ms, n_rays, rays_first_chunk, m_first_chunk, thr, peaks):
+    """Algorithmic work (SURVEY.md 8d / DESIGN.md 4) / measured stage time for the first chunk of the frame."""
+    r, m = float(rays_first_chunk), float(m_first_chunk)
+    hbm = peaks["hbm_gbs"]
+    out = {}
+    def add(name, ms, work, unit, peak, bound):
+        if ms > 0:
+            ach = work / (ms * 1e-3) / (1e9 if unit == "GB/s" else 1e12)
+            out[name] = dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak)
+    add("stage0_features", stage_ms[0], r * (12 + 512 + 24), "GB/s", hbm, "hbm")          # dirs in, packed hi/lo tile + ray o/d out
+    add("mlp0", stage_ms[1], r * FLOP_PER_RAY_MLP0, "TFLOP/s", peaks["tflops"], "tensor")   # algorithmic flops (x3 MMAs issued for the split)
+    if thr > 0:
+        add("stage2_sample", stage_ms[2], r * (512 + 8) + m * 16, "GB/s", hbm, "hbm")
+    add("stage3_posenc", stage_ms[3], m * (8 + 256) + r * 24, "GB/s", hbm, "hbm")           # (ray, z) in, packed bf16 P+V blocks out
+    add("mlp1", stage_ms[4], m * FLOP_PER_SAMPLE_MLP1, "TFLOP/s", peaks["tflops"], "tensor")
+    add("stage5_composite", stage_ms[5], m * 20 + r * 20, "GB/s", hbm, "hbm")
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -279,9 +308,12 @@ def run_ours(args, cfg, name):
             clocks=clocks,
             stage_ms=dict(zip(["stage0_features", "mlp0", "stage2_sample", "stage3_posenc", "mlp1", "stage5_composite"],
                               [round(float(x), 4) for x in stage_ms])),
-            roofline=dict(kernel="mlp_umma_kernel<1,2> (shading MLP, first chunk of the frame)", bound="tensor", achieved=achieved,
-                          peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=None,
+            roofline=dict(kernel="mlp_umma_kernel<1,2,2> (shading MLP, first chunk of the frame)", bound="tensor", achieved=achieved,
+                          peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=ncu_traffic("mlp_umma_kernel<1, 2, 2>"),
+                          traffic_unit="bytes of DRAM read+write per launch (profiles/ncu_r1_summary.json, ncu --set full)",
                           peak_source=peaks["source"]),
+            roofline_stages=stage_rooflines(stage_ms, n_rays, chunk_rays if thr == 0.0 else n_rays,
+                                            (chunk_rays * K) if thr == 0.0 else int(m_samples), thr, peaks),
             cpu_baseline=dict(value=cpu["frames_per_s"], unit="frames/s", cores=cpu["cores"], kind="port", sample=cpu["sample"]),
         )
         print(json.dumps(line))
