@@ -24,7 +24,7 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float a, float b) {
 }
 
 // Epilogue kinds (derived from the layer flags once per layer, so the per-element code is branch free).
-enum : int { EK_ACT_RELU = 0, EK_ACT_RELU_ALPHA = 1, EK_ACT_LINEAR = 2, EK_FINAL_RGB = 3, EK_FINAL_RAW = 4 };
+enum : int { EK_ACT_RELU = 0, EK_ACT_RELU_ALPHA = 1, EK_ACT_LINEAR = 2, EK_FINAL_RGB = 3, EK_FINAL_RAW = 4, EK_FINAL_RAW_STAGED = 5 };
 
 __device__ __forceinline__ int epilogue_kind(uint8_t flags) {
   if (flags & LF_FINAL_RAW) return EK_FINAL_RAW;
@@ -105,6 +105,18 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int c, c
         lo.w = pack_bf16x2(l[6], l[7]);
         st_shared_v4(act_lo + off, lo.x, lo.y, lo.z, lo.w);
       }
+    }
+  }
+  if (KIND == EK_FINAL_RAW_STAGED) {
+    // fp32 row slice -> shared-memory staging (two 32 KB pieces that the next tile's input load does not touch);
+    // 16-byte units are XOR-swizzled by the row so that both these row-wise writes and the later coalesced row
+    // reads are bank-conflict free.  The block-wide copy to global happens after the layer (see kernel).
+    const uint32_t base = act_hi + ((row_in_tile < 64) ? 2u : 6u) * kBlkBytes + uint32_t(row_in_tile & 63) * 512u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t unit = (uint32_t(c >> 2) + j) ^ uint32_t(row_in_tile & 31);
+      st_shared_v4(base + unit * 16u, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                   __float_as_uint(v[4 * j + 3]));
     }
   }
   if (KIND == EK_FINAL_RAW) {
@@ -473,7 +485,8 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       float rgb[3] = {0.0f, 0.0f, 0.0f};
       for (int l = 0; l < prog.n_layers; ++l) {
         const MlpLayer& L = prog.layers[l];
-        const int kind = epilogue_kind(L.flags);
+        int kind = epilogue_kind(L.flags);
+        if (NSPLIT == 2 && kind == EK_FINAL_RAW && prog.out_cols == 128) kind = EK_FINAL_RAW_STAGED;
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(g * 256);
         mbar_wait(&acc_full[g], acc_phase, err_flag, 5);
         acc_phase ^= 1;
@@ -503,10 +516,28 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
             case EK_FINAL_RGB:
               epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
               break;
+            case EK_FINAL_RAW_STAGED:
+              epilogue_layer<NSPLIT, EK_FINAL_RAW_STAGED>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
             default:
               epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
               break;
           }
+        }
+        if (kind == EK_FINAL_RAW_STAGED) {
+          // the tile's [128 x 128] fp32 logits are contiguous in global memory: every warp copies 8 staged rows, one
+          // fully coalesced 512-byte row per instruction
+          named_bar_sync(1 + g, EW * 32);
+#pragma unroll
+          for (int i = 0; i < 128 / EW; ++i) {
+            const int row = e * (128 / EW) + i;
+            const long long gr = t * kTileM + row;
+            const uint32_t src = act_hi + ((row < 64) ? 2u : 6u) * kBlkBytes + uint32_t(row & 63) * 512u + ((uint32_t(lane) ^ uint32_t(row & 31)) << 4);
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(src));
+            if (gr < rows) reinterpret_cast<uint4*>(out + gr * 128)[lane] = q;
+          }
+          named_bar_sync(1 + g, EW * 32);   // staging area is reused by the next tile's hidden activations
         }
         if (L.flags & LF_FINAL_RGB) {
           // The QW warps of a lane quarter hold partial alpha / rgb dot products over their column slices:
