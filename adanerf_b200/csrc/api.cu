@@ -160,8 +160,14 @@ struct Seg {
 // 128-row N half: a [128 x 64] K-major SWIZZLE_128B bf16 tile (hi), followed by the lo tile when nsplit == 2.
 void pack_layer(const float* W, int n_out, int k_in, const std::vector<Seg>& segs, int nsplit, std::vector<uint8_t>& blob) {
   const int n_half = (n_out + 127) / 128;
-  for (const Seg& sg : segs) {
-    for (int nh = 0; nh < n_half; ++nh) {
+  // stage order = consumption order: the half-pipelined split-precision kernel walks N half outermost (half 0's
+  // accumulator completes first), the bf16 kernel K block outermost (both halves of a K block form one stage)
+  const bool nh_outer = (nsplit == 2);
+  const int n_seg = int(segs.size());
+  for (int o = 0; o < (nh_outer ? n_half : n_seg); ++o) {
+    for (int i = 0; i < (nh_outer ? n_seg : n_half); ++i) {
+      const int nh = nh_outer ? o : i;
+      const Seg& sg = segs[nh_outer ? i : o];
       const size_t base = blob.size();
       blob.resize(base + size_t(nsplit) * kBlkBytes, 0);
       for (int n = 0; n < 128; ++n) {

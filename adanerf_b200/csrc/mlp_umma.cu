@@ -585,6 +585,316 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
 }
 
 // -------------------------------------------------------------------------------------------------
+// Half-pipelined variant for the split-precision sampling net (NSPLIT = 2, one tile per CTA).
+//
+// One tile does not leave room for a second slot (its hi + lo activations are 128 KB), so the overlap comes from
+// inside the layer: every layer's N is produced as two 128-column halves, half 0's epilogue runs while half 1's
+// MMAs are still executing, and the next layer's first two K blocks (written by half 0) start while half 1's
+// epilogue is still running.  What makes this safe:
+//   * accumulators are double buffered in TMEM by a running layer counter (layers G and G+1 never share columns),
+//   * hidden activations are still updated in place, so half 0's epilogue may only STORE once the last MMA of the
+//     layer that reads hidden blocks 0,1 has retired -- the issuer commits `lo_free` right after those MMAs,
+//   * half 1's epilogue writes blocks 2,3 only after all MMAs of the layer have retired (acc_full[1]).
+// The next tile's layer 0 needs nothing but its input tile, so a tile's last epilogue overlaps the next tile's
+// first MMAs.  Weights are packed N-half outermost for this kernel (adn_set_weights).
+template <int CG>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_hp_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict__ wblob,
+              const uint8_t* __restrict__ in_tiles, float* __restrict__ out,
+              const long long* __restrict__ rows_dev, long long rows_host, int* err_flag, long long* trace) {
+  constexpr int NSPLIT = 2;
+  using Ring = RingCfg<NSPLIT, CG>;
+  constexpr int NB = MlpCfg<NSPLIT>::kNB;
+  constexpr int STAGES = Ring::kStages;
+  constexpr int STAGE_BYTES = Ring::kStageBytes;
+  constexpr int HALF = kBlkBytes / CG;
+  constexpr int EW = 16, QW = 4, CW = 32;
+  constexpr int kProducerWarp = 16, kHelperWarp = 17, kMmaWarp = 18;
+  constexpr int kBarHalf = 3, kBarStage = 5;   // named barrier ids (1 is used by the epilogue warps)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* act = smem;                                                   // [NSPLIT][NB] blocks
+  uint8_t* ring = act + size_t(NSPLIT) * NB * kBlkBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(STAGES) * STAGE_BYTES);
+  uint64_t* w_full = bars;                     // [STAGES]
+  uint64_t* w_empty = w_full + STAGES;         // [STAGES]
+  uint64_t* peer_full = w_empty + STAGES;      // [STAGES] leader only
+  uint64_t* acc_full = peer_full + STAGES;     // [2]  accumulator half complete
+  uint64_t* act_ready = acc_full + 2;          // [2]  this CTA's epilogue of that half is done (A blocks written)
+  uint64_t* peer_act = act_ready + 2;          // [2]  leader only
+  uint64_t* lo_free = peer_act + 2;            // [1]  hidden blocks 0,1 are no longer read by this layer's MMAs
+  uint64_t* in_full = lo_free + 1;             // [1]
+  uint64_t* peer_in = in_full + 1;             // [1]  leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_in + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  const long long n_units = gridDim.x / CG;
+  const long long unit = blockIdx.x / CG;
+  const long long rows = rows_dev ? *rows_dev : rows_host;
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+  const int n_layers = prog.n_layers;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+      mbar_init(&peer_full[s], 1);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&acc_full[h], 1);
+      mbar_init(&act_ready[h], EW);
+      mbar_init(&peer_act[h], 1);
+    }
+    mbar_init(lo_free, 1);
+    mbar_init(in_full, 1);
+    mbar_init(peer_in, 1);
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc_cg<CG>(tmem_slot, 512);
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto act_ptr = [&](int term, int blk) -> uint8_t* { return act + (size_t(term) * NB + blk) * kBlkBytes; };
+  auto first_tile = [&](long long iter) -> long long { return (iter * n_units + unit) * CG; };
+  (void)trace;
+
+  if (warp == kProducerWarp) {
+    // ===================================================================== weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long iter = 0;; ++iter) {
+        if (first_tile(iter) >= n_tiles) break;
+        for (int l = 0; l < n_layers; ++l) {
+          const MlpLayer& L = prog.layers[l];
+          const int n_st = int(L.n_kb) * int(L.n_half);
+          const uint8_t* src = wblob + L.w_off;
+          for (int i = 0; i < n_st; ++i) {
+            mbar_wait(&w_empty[stage], phase ^ 1, err_flag, 1);
+            uint8_t* dst = ring + size_t(stage) * STAGE_BYTES;
+            const uint8_t* s0 = src + size_t(i) * (2 * kBlkBytes);
+            mbar_arrive_expect_tx(&w_full[stage], 2 * HALF);
+            bulk_g2s(dst, s0 + cta_rank * HALF, HALF, &w_full[stage]);
+            bulk_g2s(dst + HALF, s0 + kBlkBytes + cta_rank * HALF, HALF, &w_full[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kHelperWarp) {
+    // =================================================================== barrier helper (see mlp_umma_kernel)
+    int stage = 0;
+    uint32_t phase = 0, in_phase = 0, ar_phase[2] = {0, 0};
+    for (long long iter = 0;; ++iter) {
+      if (first_tile(iter) >= n_tiles) break;
+      for (int l = 0; l < n_layers; ++l) {
+        const MlpLayer& L = prog.layers[l];
+        if (l == 0) {
+          mbar_wait(in_full, in_phase, err_flag, 2);
+          if (CG == 2) {
+            if (leader) mbar_wait(peer_in, in_phase, err_flag, 7);
+            else if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(peer_in), 0));
+          }
+          in_phase ^= 1;
+          if (leader) named_bar_arrive(kBarHalf, 64);
+        }
+        bool seen[2] = {l == 0, l == 0};
+        for (int nh = 0; nh < L.n_half; ++nh) {
+          for (int kb = 0; kb < L.n_kb; ++kb) {
+            const int h = int(L.a_blk[kb]) >> 1;   // hidden blocks 0,1 <- half 0 of the previous layer, 2,3 <- half 1
+            if (!seen[h]) {
+              seen[h] = true;
+              mbar_wait(&act_ready[h], ar_phase[h], err_flag, 3);
+              if (CG == 2) {
+                if (leader) mbar_wait(&peer_act[h], ar_phase[h], err_flag, 9);
+                else if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&peer_act[h]), 0));
+              }
+              ar_phase[h] ^= 1;
+              if (leader) named_bar_arrive(kBarHalf + h, 64);
+            }
+            mbar_wait(&w_full[stage], phase, err_flag, 4);
+            if (CG == 2) {
+              if (leader) mbar_wait(&peer_full[stage], phase, err_flag, 8);
+              else if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&peer_full[stage]), 0));
+            }
+            if (leader) named_bar_arrive(kBarStage + stage, 64);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ========================================================================== MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc128 = make_idesc_bf16(128 * CG, 128);
+      int stage = 0;
+      uint32_t gl = 0;   // running layer counter: selects the TMEM accumulator buffer
+      const uint64_t desc_hi = make_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+      const uint32_t desc_lo_const = uint32_t(make_desc_sw128(0) & 0xFFFF0000ull);
+      auto lo_of = [&](uint32_t addr) -> uint32_t { return desc_lo_const | (addr >> 4); };
+      const uint32_t ring_lo = lo_of(smem_u32(ring));
+      const uint32_t act_lo0 = lo_of(smem_u32(act));
+      auto desc = [&](uint32_t lo) -> uint64_t { return desc_hi | uint64_t(lo); };
+      for (long long iter = 0;; ++iter) {
+        if (first_tile(iter) >= n_tiles) break;
+        for (int l = 0; l < n_layers; ++l, ++gl) {
+          const MlpLayer& L = prog.layers[l];
+          const bool final_layer = (l + 1 == n_layers);
+          uint32_t blks = 0;
+#pragma unroll
+          for (int kb = 0; kb < 6; ++kb) blks |= uint32_t(L.a_blk[kb] & 15) << (4 * kb);
+          if (l == 0) {
+            named_bar_sync(kBarHalf, 64);   // input tile landed (both CTAs)
+            tc_fence_after();
+          }
+          bool seen[2] = {l == 0, l == 0};
+          const uint32_t d_layer = tmem_base + (gl & 1u) * 256u;
+          for (int nh = 0; nh < L.n_half; ++nh) {
+            for (int kb = 0; kb < L.n_kb; ++kb) {
+              const uint32_t blk = (blks >> (4 * kb)) & 15u;
+              const int h = int(blk >> 1);
+              if (!seen[h]) {
+                seen[h] = true;
+                named_bar_sync(kBarHalf + h, 64);   // previous layer's half h has been published by both CTAs
+                tc_fence_after();
+              }
+              const uint32_t a_hi = act_lo0 + blk * (kBlkBytes >> 4);
+              const uint32_t a_lo = a_hi + uint32_t(NB) * (kBlkBytes >> 4);
+              named_bar_sync(kBarStage + stage, 64);
+              tc_fence_after();
+              const uint32_t b_hi = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
+              const uint32_t b_lo = b_hi + (HALF >> 4);
+              const uint32_t d = d_layer + uint32_t(nh * 128);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_hi + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
+                  umma_bf16_cg<CG>(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
+                  umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
+                }
+                umma_commit_cg<CG>(&w_empty[stage]);
+                // the last MMAs of this layer that read hidden blocks 0,1 have been issued: half 0's epilogue may store
+                if (!final_layer && nh == L.n_half - 1 && kb == 1) umma_commit_cg<CG>(lo_free);
+              }
+              __syncwarp();
+              if (++stage == STAGES) stage = 0;
+            }
+            if (elect_one()) umma_commit_cg<CG>(&acc_full[nh]);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ============================================================================ epilogue (16 warps, one tile)
+    const int e = warp;                            // 0..15
+    const int quarter = warp & 3;
+    const int sub = e >> 2;                        // 32-column slice of each N half
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t acc_ph[2] = {0, 0}, lo_ph = 0, gl = 0;
+    const uint32_t act_hi = smem_u32(act_ptr(0, 0));
+    const uint32_t act_lo = smem_u32(act_ptr(1, 0));
+    float alpha = 0.f, rgb[3] = {0.f, 0.f, 0.f};
+    for (long long iter = 0;; ++iter) {
+      const long long t0 = first_tile(iter);
+      if (t0 >= n_tiles) break;
+      const long long t = t0 + cta_rank;
+      const bool have_tile = t < n_tiles;
+      const long long grow = t * kTileM + row_in_tile;
+      if (e == 0 && lane == 0) {
+        // safe: this warp has seen acc_full of the previous tile's last half, i.e. every MMA reading blocks 0,1 retired
+        if (have_tile) {
+          const uint8_t* src = in_tiles + size_t(t) * prog.in_tile_stride;
+          const uint32_t bytes = uint32_t(prog.in0_nblk) * kBlkBytes;
+          mbar_arrive_expect_tx(in_full, bytes * NSPLIT);
+          bulk_g2s(act_ptr(0, prog.in0_blk), src + prog.in0_off, bytes, in_full);
+          bulk_g2s(act_ptr(1, prog.in0_blk), src + prog.in0_lo_off, bytes, in_full);
+        } else {
+          mbar_arrive(in_full);
+        }
+      }
+      for (int l = 0; l < n_layers; ++l, ++gl) {
+        const MlpLayer& L = prog.layers[l];
+        const bool final_layer = (l + 1 == n_layers);
+        int kind = epilogue_kind(L.flags);
+        if (kind == EK_FINAL_RAW && prog.out_cols == 128) kind = EK_FINAL_RAW_STAGED;
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + (gl & 1u) * 256u;
+        for (int h = 0; h < L.n_half; ++h) {
+          mbar_wait(&acc_full[h], acc_ph[h], err_flag, 5);
+          acc_ph[h] ^= 1;
+          tc_fence_after();
+          const int c = h * 128 + sub * CW;
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tc_wait_ld();
+          if (h == 0 && !final_layer) {   // in-place hazard: hidden blocks 0,1 may still feed this layer's half-1 MMAs
+            mbar_wait(lo_free, lo_ph, err_flag, 6);
+            lo_ph ^= 1;
+          }
+          switch (kind) {
+            case EK_ACT_RELU:
+              epilogue_chunk<NSPLIT, EK_ACT_RELU>(r, c, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+            case EK_ACT_LINEAR:
+              epilogue_chunk<NSPLIT, EK_ACT_LINEAR>(r, c, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+            case EK_FINAL_RAW_STAGED:
+              epilogue_chunk<NSPLIT, EK_FINAL_RAW_STAGED>(r, c, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+            default:
+              epilogue_chunk<NSPLIT, EK_FINAL_RAW>(r, c, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+              break;
+          }
+          if (!final_layer) {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&act_ready[h]);
+          }
+        }
+        if (final_layer) {
+          // every epilogue warp meets here once per tile: the staged logits are complete (and, for tiny test nets,
+          // nobody is still reading an accumulator buffer that the next tile's first layers will overwrite)
+          tc_fence_before();
+          named_bar_sync(1, EW * 32);
+          if (kind == EK_FINAL_RAW_STAGED) {
+#pragma unroll
+            for (int i = 0; i < 128 / EW; ++i) {
+              const int row = e * (128 / EW) + i;
+              const long long gr = t * kTileM + row;
+              const uint32_t src = act_hi + ((row < 64) ? 2u : 6u) * kBlkBytes + uint32_t(row & 63) * 512u + ((uint32_t(lane) ^ uint32_t(row & 31)) << 4);
+              uint4 q;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(src));
+              if (gr < rows) reinterpret_cast<uint4*>(out + gr * 128)[lane] = q;
+            }
+            named_bar_sync(1, EW * 32);   // staging area = hidden blocks 2,3, rewritten by the next tile's layer-0 epilogue
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_cg<CG>(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // fp32 feature rows [rows, n_feat] -> packed bf16 (hi / lo) SWIZZLE_128B tile blocks.
 // One thread per (row, block, 16-byte chunk): 8 consecutive source columns.
 __global__ void pack_rows_kernel(const float* __restrict__ x, long long rows_host, const long long* __restrict__ rows_dev,
@@ -665,14 +975,48 @@ static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, co
   return cudaLaunchKernelEx(&cfg, kernel, prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, trace);
 }
 
+template <int CG>
+static cudaError_t launch_hp_t(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles, float* out,
+                               const long long* rows_dev, long long rows_host, int* err_flag, int num_sms, cudaStream_t stream,
+                               long long* trace) {
+  static bool attr_set = false;
+  const size_t smem = mlp_smem_layout_bytes<2, 1, CG>();
+  auto kernel = mlp_hp_kernel<CG>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int grid = (num_sms / CG) * CG;
+  if (!rows_dev) {
+    const long long n_tiles = (rows_host + kTileM - 1) / kTileM;
+    const long long need = ((n_tiles + CG - 1) / CG) * CG;
+    if (need < grid) grid = int(need < CG ? CG : need);
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(kMlpThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, trace);
+}
+
 cudaError_t launch_mlp(int nsplit, int ng, int cg, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host, int* err_flag,
                        int num_sms, cudaStream_t stream, long long* trace) {
-  if (cg == 2) {
-    if (nsplit == 2) return launch_mlp_t<2, 1, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
-    return launch_mlp_t<1, 2, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+  // split precision (sampling net): half-pipelined single-tile kernel; weights packed N-half outermost
+  if (nsplit == 2) {
+    if (cg == 2) return launch_hp_t<2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+    return launch_hp_t<1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
   }
-  if (nsplit == 2) return launch_mlp_t<2, 1, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
+  if (cg == 2) return launch_mlp_t<1, 2, 2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
   return launch_mlp_t<1, 2, 1>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);
 }
 
