@@ -748,6 +748,7 @@ adn_status adn_get_stats(adn_ctx* ctx, adn_stats* out) {
 
 adn_status adn_render_rays(adn_ctx* ctx, const float* pose, const float* rot, const float* d_dirs, int64_t n_rays, float thr,
                            int K, float* d_rgb, int32_t* d_nsamples, float* d_oracle_weights, void* stream) {
+  if (ctx && n_rays == 0) return ADN_OK;   // empty batch: nothing to read or write
   if (!d_dirs) return fail(ctx, ADN_ERR_INVALID, "render_rays: d_dirs is null");
   return render_impl(ctx, pose, rot, d_dirs, nullptr, n_rays, thr, K, d_rgb, nullptr, d_nsamples, d_oracle_weights,
                      static_cast<cudaStream_t>(stream));

@@ -380,3 +380,21 @@ def test_threshold_sweep_vs_oracle(K, pavillon_weights):
         print(f"K={K} thr={thr}: mean spr {ref['n_samples'].float().mean():.2f}, identical counts {same:.4f}, PSNR {p:.2f} dB")
         assert same >= 0.99 and p >= 50.0
     r.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 127, 129, 257, 385])
+def test_render_ragged_sizes(n):
+    """Ray counts around the 128-row tile / CTA-pair boundaries (odd tile counts leave one CTA of a pair without a
+    tile) and the empty call."""
+    scene = orc.SCENE_BARBERSHOP
+    sd0, sd1 = orc.make_weights("shaped", seed=0)
+    r = _renderer(scene, sd0, sd1)
+    pose, rot = torch.tensor(scene["view_cell_center"]), torch.eye(3)
+    dirs = torch.from_numpy(orc.generate_ray_directions(800, 800, scene["fov"]).reshape(-1, 3)).float()[::1663][:n]
+    out = r.render_rays(pose, rot, dirs.cuda(), 0.2, 8)
+    assert out["rgb"].shape == (n, 3)
+    if n:
+        ref = orc.render_rays(pose, rot, dirs, sd0, sd1, scene, 0.2, 8)
+        assert torch.equal(out["n_samples"].cpu().long(), ref["n_samples"])
+        assert np.abs(out["rgb"].cpu().numpy() - ref["rgb"].numpy()).max() < 5e-3
+    r.close()
