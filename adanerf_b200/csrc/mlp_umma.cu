@@ -162,6 +162,15 @@ __device__ __forceinline__ void epilogue_layer(uint32_t taddr, int c0, int span,
 // of [128 x 64] hi + lo.  CG = 2 (CTA pair, cta_group::2 MMAs with M = 256): every CTA streams only ITS half of the
 // B rows of each stage, so the same 64 / 96 KB hold twice as many stages (4 / 6): three or more weight stages are in
 // flight while one is consumed, and each SM pulls half the weight bytes from L2.
+// Ring stages a layer consumes.  Split precision: one per (K block, N half).  Plain bf16: one per K block for
+// 256-wide layers; 128-wide layers pack TWO K blocks into a stage (same bytes as one wide K block), so every
+// barrier round trip of the issuer still carries 8 x 64 = 512 tensor cycles of work.
+template <int NSPLIT>
+__device__ __forceinline__ int layer_stages(const MlpLayer& L) {
+  if (NSPLIT == 2) return int(L.n_kb) * int(L.n_half);
+  return (L.n_half == 2) ? int(L.n_kb) : (int(L.n_kb) + 1) / 2;
+}
+
 template <int NSPLIT, int CG>
 struct RingCfg {
   static constexpr int kStageBytes = 2 * kBlkBytes / CG;
@@ -269,8 +278,8 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         if (first_tile(iter, 0) >= n_tiles) break;
         for (int l = 0; l < prog.n_layers; ++l) {
           const MlpLayer& L = prog.layers[l];
-          const int n_st = (NSPLIT == 2) ? int(L.n_kb) * int(L.n_half) : int(L.n_kb);
-          const uint32_t src_stride = (NSPLIT == 2) ? uint32_t(2 * kBlkBytes) : uint32_t(L.n_half) * kBlkBytes;
+          const int n_st = layer_stages<NSPLIT>(L);
+          const uint32_t src_stride = (NSPLIT == 2 || L.n_half == 2) ? uint32_t(2 * kBlkBytes) : uint32_t(kBlkBytes);
           for (int g = 0; g < NG; ++g) {
             if (first_tile(iter, g) >= n_tiles) continue;
             const uint8_t* src = wblob + L.w_off;
@@ -295,8 +304,12 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
                   bulk_g2s(dst, s0, 2 * kBlkBytes, &w_full[stage]);
                 }
               } else {
-                mbar_arrive_expect_tx(&w_full[stage], HALF);
-                bulk_g2s(dst, s0 + cta_rank * HALF, HALF, &w_full[stage]);
+                // 128-wide layer: K blocks 2i and 2i+1 (if present) share the stage, each as this CTA's row range
+                const int nkb = (2 * i + 1 < int(L.n_kb)) ? 2 : 1;
+                const uint8_t* s1 = src + size_t(2 * i) * kBlkBytes;
+                mbar_arrive_expect_tx(&w_full[stage], uint32_t(nkb) * HALF);
+                bulk_g2s(dst, s1 + cta_rank * HALF, HALF, &w_full[stage]);
+                if (nkb == 2) bulk_g2s(dst + HALF, s1 + kBlkBytes + cta_rank * HALF, HALF, &w_full[stage]);
               }
               if (++stage == STAGES) {
                 stage = 0;
@@ -322,7 +335,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       if (first_tile(iter, 0) >= n_tiles) break;
       for (int l = 0; l < prog.n_layers; ++l) {
         const MlpLayer& L = prog.layers[l];
-        const int n_st = (NSPLIT == 2) ? int(L.n_kb) * int(L.n_half) : int(L.n_kb);
+        const int n_st = layer_stages<NSPLIT>(L);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           if (first_tile(iter, g) >= n_tiles) continue;
@@ -403,21 +416,34 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
                 tc_fence_after();
                 if (lane == 0 && l == 2) tr(0, g, kb, 6);
                 const uint32_t b = ring_lo + uint32_t(stage) * (STAGE_BYTES >> 4);
-                if (elect_one()) {
-                  if (wide) {
+                bool two = false;
+                if (wide) {   // hot path: kept minimal, the issuer warp's instruction count is the kernel's clock
+                  if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                       umma_bf16_cg<CG>(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc256, (kb > 0 || k > 0) ? 1u : 0u);
-                  } else {
+                    umma_commit_cg<CG>(&w_empty[stage]);
+                  }
+                } else {
+                  // 128-wide layer: this stage also carries the next K block (if the layer has one)
+                  two = (kb + 1 < L.n_kb);
+                  const uint32_t a_hi2 = act_lo0 + (uint32_t(g * NSPLIT * NB) + ((blks >> (4 * (kb + 1))) & 15u)) * (kBlkBytes >> 4);
+                  if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                       umma_bf16_cg<CG>(d0, desc(a_hi + 2 * k), desc(b + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
+                    if (two) {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        umma_bf16_cg<CG>(d0, desc(a_hi2 + 2 * k), desc(b + (HALF >> 4) + 2 * k), idesc128, 1u);
+                    }
+                    umma_commit_cg<CG>(&w_empty[stage]);
                   }
-                  umma_commit_cg<CG>(&w_empty[stage]);
                 }
                 __syncwarp();
                 if (lane == 0 && l == 2) tr(0, g, kb, 7);
                 if (++stage == STAGES) stage = 0;
+                if (two) ++kb;
               } else {
                 for (int nh = 0; nh < L.n_half; ++nh) {
                   named_bar_sync(kBarStage + stage, 64);
