@@ -194,7 +194,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   constexpr int STAGES = Ring::kStages;
   constexpr int STAGE_BYTES = Ring::kStageBytes;
   constexpr int HALF = kBlkBytes / CG;   // bytes of one [128 x 64] B tile held by one CTA
-  constexpr int EW = 16 / NG;   // epilogue warps per tile slot
+  constexpr int EW = 16;        // epilogue warps: every one of them serves all NG tile slots in turn
   constexpr int QW = EW / 4;    // warps sharing one TMEM lane quarter (they split the columns)
   constexpr int CW = 128 / QW;  // accumulator columns per warp and N half
   constexpr int kProducerWarp = 16, kHelperWarp = 17, kMmaWarp = 18;   // highest warp ids: favoured by the issue arbiter
@@ -474,25 +474,21 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     }
   } else {
     // ============================================================================ epilogue
-    const int ew = warp;                           // 0..15
-    const int g = ew / EW;                         // tile slot
-    const int e = ew % EW;                         // index inside the slot's warp set
+    // All 16 warps serve BOTH tile slots, alternating (layer l slot 0, layer l slot 1, layer l+1 slot 0, ...): the
+    // slots' accumulators become ready one after the other (the issuer alternates too), so each epilogue is done by
+    // twice the warps in half the time and the slot's MMA -> epilogue -> MMA chain gets shorter than the two slots'
+    // tensor time -- the tensor pipe, not the chain, then sets the pace.
+    const int e = warp;                            // 0..15
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int sub = e >> 2;                        // which column slice of each N half this warp owns
     const int row_in_tile = quarter * 32 + lane;
-    uint32_t acc_phase = 0;
-    const uint32_t act_hi = smem_u32(act_ptr(g, 0, 0));
-    const uint32_t act_lo = smem_u32(act_ptr(g, NSPLIT - 1, 0));
-    // act_ready is local to every CTA (cheap release.cta arrive); in a CTA pair the peer's helper warp forwards it
-    auto arrive_act_ready = [&]() { mbar_arrive(&act_ready[g]); };
-    for (long long iter = 0;; ++iter) {
-      const long long t0 = first_tile(iter, g);
-      if (t0 >= n_tiles) break;
-      const long long t = t0 + cta_rank;           // may be one past the end in the last pair: rows masked, protocol kept
-      const bool have_tile = t < n_tiles;
-      const long long grow = t * kTileM + row_in_tile;
+    uint32_t acc_phase = 0;                        // bit g = parity of acc_full[g]
+    float alpha_s0 = 0.0f, alpha_s1 = 0.0f;        // per-slot alpha partial (layer 7 -> final layer)
+    // tile prologue of slot g: load its input tile and hand the (free) accumulator / activation buffers to layer 0
+    auto tile_prologue = [&](long long iter, int g) {
+      const long long t = first_tile(iter, g) + cta_rank;
       if (e == 0 && lane == 0) {
-        if (have_tile) {
+        if (t < n_tiles) {
           const uint8_t* src = in_tiles + size_t(t) * prog.in_tile_stride;
           const uint32_t bytes = uint32_t(prog.in0_nblk) * kBlkBytes;
           mbar_arrive_expect_tx(&in_full[g], bytes * NSPLIT);
@@ -502,101 +498,119 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
           mbar_arrive(&in_full[g]);
         }
       }
-      // accumulator columns and activation buffers of this slot are free for layer 0
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) arrive_act_ready();
-
-      float alpha = 0.0f;
-      float rgb[3] = {0.0f, 0.0f, 0.0f};
+      if (lane == 0) mbar_arrive(&act_ready[g]);   // local; in a CTA pair the peer's helper warp forwards it
+    };
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g)
+      if (first_tile(0, g) < n_tiles) tile_prologue(0, g);
+    for (long long iter = 0;; ++iter) {
+      if (first_tile(iter, 0) >= n_tiles) break;
       for (int l = 0; l < prog.n_layers; ++l) {
         const MlpLayer& L = prog.layers[l];
         int kind = epilogue_kind(L.flags);
         if (NSPLIT == 2 && kind == EK_FINAL_RAW && prog.out_cols == 128) kind = EK_FINAL_RAW_STAGED;
-        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(g * 256);
-        mbar_wait(&acc_full[g], acc_phase, err_flag, 5);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 3);
-        if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
-          if (have_tile) {
-            mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
-            bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
-                     &in_full[g]);
-          } else {
-            mbar_arrive(&in_full[g]);
-          }
-        }
-        for (int h = 0; h < L.n_half; ++h) {
-          const int c0 = h * 128 + sub * CW;
-          switch (kind) {
-            case EK_ACT_RELU:
-              epilogue_layer<NSPLIT, EK_ACT_RELU>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-              break;
-            case EK_ACT_RELU_ALPHA:
-              epilogue_layer<NSPLIT, EK_ACT_RELU_ALPHA>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-              break;
-            case EK_ACT_LINEAR:
-              epilogue_layer<NSPLIT, EK_ACT_LINEAR>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-              break;
-            case EK_FINAL_RGB:
-              epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-              break;
-            case EK_FINAL_RAW_STAGED:
-              epilogue_layer<NSPLIT, EK_FINAL_RAW_STAGED>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-              break;
-            default:
-              epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
-              break;
-          }
-        }
-        if (kind == EK_FINAL_RAW_STAGED) {
-          // the tile's [128 x 128] fp32 logits are contiguous in global memory: every warp copies 8 staged rows, one
-          // fully coalesced 512-byte row per instruction
-          named_bar_sync(1 + g, EW * 32);
-#pragma unroll
-          for (int i = 0; i < 128 / EW; ++i) {
-            const int row = e * (128 / EW) + i;
-            const long long gr = t * kTileM + row;
-            const uint32_t src = act_hi + ((row < 64) ? 2u : 6u) * kBlkBytes + uint32_t(row & 63) * 512u + ((uint32_t(lane) ^ uint32_t(row & 31)) << 4);
-            uint4 q;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(src));
-            if (gr < rows) reinterpret_cast<uint4*>(out + gr * 128)[lane] = q;
-          }
-          named_bar_sync(1 + g, EW * 32);   // staging area is reused by the next tile's hidden activations
-        }
-        if (L.flags & LF_FINAL_RGB) {
-          // The QW warps of a lane quarter hold partial alpha / rgb dot products over their column slices:
-          // combine them through shared memory (the slot's hidden blocks are dead once this layer's MMAs
-          // have retired) and let the sub == 0 warp write the row.
-          if (QW > 1) {
-            float4* scratch = reinterpret_cast<float4*>(act_ptr(g, 0, prog.hid_blk0));
-            if (sub > 0) scratch[(sub - 1) * kTileM + row_in_tile] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
-            named_bar_sync(1 + g, EW * 32);
-            if (sub == 0) {
-#pragma unroll
-              for (int q = 1; q < QW; ++q) {
-                const float4 p = scratch[(q - 1) * kTileM + row_in_tile];
-                rgb[0] += p.x;
-                rgb[1] += p.y;
-                rgb[2] += p.z;
-                alpha += p.w;
-              }
+#pragma unroll 1
+        for (int g = 0; g < NG; ++g) {
+          const long long t0 = first_tile(iter, g);
+          if (t0 >= n_tiles) continue;
+          const long long t = t0 + cta_rank;         // may be one past the end in the last pair: rows masked, protocol kept
+          const bool have_tile = t < n_tiles;
+          const long long grow = t * kTileM + row_in_tile;
+          const uint32_t act_hi = smem_u32(act_ptr(g, 0, 0));
+          const uint32_t act_lo = smem_u32(act_ptr(g, NSPLIT - 1, 0));
+          const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(g * 256);
+          float alpha = (g == 0) ? alpha_s0 : alpha_s1;
+          float rgb[3] = {0.0f, 0.0f, 0.0f};
+          if (l == 0) alpha = 0.0f;
+          mbar_wait(&acc_full[g], (acc_phase >> g) & 1u, err_flag, 5);
+          acc_phase ^= (1u << g);
+          tc_fence_after();
+          if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 3);
+          if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
+            if (have_tile) {
+              mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
+              bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
+                       &in_full[g]);
+            } else {
+              mbar_arrive(&in_full[g]);
             }
-            named_bar_sync(1 + g, EW * 32);
           }
-          if (sub == 0 && grow < rows) {
-            const float ab = prog.side[prog.alpha_b_off];
-            const float b0 = prog.side[prog.rgb_b_off], b1 = prog.side[prog.rgb_b_off + 1], b2 = prog.side[prog.rgb_b_off + 2];
-            reinterpret_cast<float4*>(out)[grow] = make_float4(rgb[0] + b0, rgb[1] + b1, rgb[2] + b2, alpha + ab);
+          for (int h = 0; h < L.n_half; ++h) {
+            const int c0 = h * 128 + sub * CW;
+            switch (kind) {
+              case EK_ACT_RELU:
+                epilogue_layer<NSPLIT, EK_ACT_RELU>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              case EK_ACT_RELU_ALPHA:
+                epilogue_layer<NSPLIT, EK_ACT_RELU_ALPHA>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              case EK_ACT_LINEAR:
+                epilogue_layer<NSPLIT, EK_ACT_LINEAR>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              case EK_FINAL_RGB:
+                epilogue_layer<NSPLIT, EK_FINAL_RGB>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              case EK_FINAL_RAW_STAGED:
+                epilogue_layer<NSPLIT, EK_FINAL_RAW_STAGED>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+              default:
+                epilogue_layer<NSPLIT, EK_FINAL_RAW>(taddr, c0, CW, L, prog, act_hi, act_lo, row_in_tile, grow, rows, out, alpha, rgb);
+                break;
+            }
           }
-        }
-        if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
-        if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 4);
-        if (l + 1 < prog.n_layers) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) arrive_act_ready();
+          if (kind == EK_FINAL_RAW_STAGED) {
+            // the tile's [128 x 128] fp32 logits are contiguous in global memory: every warp copies 8 staged rows, one
+            // fully coalesced 512-byte row per instruction
+            named_bar_sync(1, EW * 32);
+#pragma unroll
+            for (int i = 0; i < 128 / EW; ++i) {
+              const int row = e * (128 / EW) + i;
+              const long long gr = t * kTileM + row;
+              const uint32_t src = act_hi + ((row < 64) ? 2u : 6u) * kBlkBytes + uint32_t(row & 63) * 512u + ((uint32_t(lane) ^ uint32_t(row & 31)) << 4);
+              uint4 q;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(src));
+              if (gr < rows) reinterpret_cast<uint4*>(out + gr * 128)[lane] = q;
+            }
+            named_bar_sync(1, EW * 32);   // staging area is reused by the next tile's hidden activations
+          }
+          if (L.flags & LF_FINAL_RGB) {
+            // The QW warps of a lane quarter hold partial alpha / rgb dot products over their column slices:
+            // combine them through shared memory (the slot's hidden blocks are dead once this layer's MMAs
+            // have retired) and let the sub == 0 warp write the row.
+            if (QW > 1) {
+              float4* scratch = reinterpret_cast<float4*>(act_ptr(g, 0, prog.hid_blk0));
+              if (sub > 0) scratch[(sub - 1) * kTileM + row_in_tile] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
+              named_bar_sync(1, EW * 32);
+              if (sub == 0) {
+#pragma unroll
+                for (int q = 1; q < QW; ++q) {
+                  const float4 p = scratch[(q - 1) * kTileM + row_in_tile];
+                  rgb[0] += p.x;
+                  rgb[1] += p.y;
+                  rgb[2] += p.z;
+                  alpha += p.w;
+                }
+              }
+              named_bar_sync(1, EW * 32);
+            }
+            if (sub == 0 && grow < rows) {
+              const float ab = prog.side[prog.alpha_b_off];
+              const float b0 = prog.side[prog.rgb_b_off], b1 = prog.side[prog.rgb_b_off + 1], b2 = prog.side[prog.rgb_b_off + 2];
+              reinterpret_cast<float4*>(out)[grow] = make_float4(rgb[0] + b0, rgb[1] + b1, rgb[2] + b2, alpha + ab);
+            }
+          }
+          if (L.flags & LF_OUT_ACT) fence_proxy_async_smem();
+          if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 4);
+          if (g == 0) alpha_s0 = alpha; else alpha_s1 = alpha;
+          if (l + 1 < prog.n_layers) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&act_ready[g]);
+          } else if (first_tile(iter + 1, g) < n_tiles) {
+            tile_prologue(iter + 1, g);   // the slot's next tile starts right away, not after the other slot's last layer
+          }
         }
       }
     }

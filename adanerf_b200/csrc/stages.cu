@@ -277,48 +277,12 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
   return v;
 }
 
-__global__ void __launch_bounds__(kS2Threads)
-stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K, const float* __restrict__ zlut,
-              int32_t* __restrict__ count, int32_t* __restrict__ offset, int32_t* __restrict__ cell_out,
-              int32_t* __restrict__ ray_out, float* __restrict__ z_out, float* __restrict__ zp_out,
-              long long* __restrict__ total, unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
-              int n_tiles) {
-  __shared__ uint32_t s_sel[kS2Rays][4];
-  __shared__ int s_cnt[kS2Rays];
-  __shared__ int s_off[kS2Rays];
-  __shared__ long long s_prefix;
-  __shared__ int s_tile;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) s_tile = int(atomicAdd(ticket, 1u));
-  __syncthreads();
-  const int tile = s_tile;
-  const long long ray0 = (long long)tile * kS2Rays;
-
-  // phase 1: selection (the warp's 8 row loads are issued up front: 8 x 512 B in flight per warp)
-  float4 rows8[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long long r = ray0 + warp * 8 + i;
-    rows8[i] = (r < n_rays) ? __ldg(reinterpret_cast<const float4*>(raw0 + r * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rl = warp * 8 + i;
-    const long long r = ray0 + rl;
-    int cnt = 0;
-    uint32_t sel[4] = {0, 0, 0, 0};
-    if (r < n_rays) cnt = select_cells(rows8[i], thr, K, lane, sel);
-    if (lane == 0) {
-      s_cnt[rl] = cnt;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s_sel[rl][j] = sel[j];
-    }
-  }
-  __syncthreads();
-
-  // CTA scan + decoupled look-back (warp 0)
-  if (warp == 0) {
+// Exclusive scan of the tile's 64 per-ray counts (-> s_off) and decoupled look-back over the preceding tiles
+// (-> *s_prefix); executed by one full warp.  Tiles are numbered by dynamic tickets, so every predecessor a tile
+// spins on has already started.
+__device__ __forceinline__ void s2_tile_scan_lookback(const int* s_cnt, int* s_off, long long* s_prefix, int tile, int n_tiles,
+                                                      int lane, unsigned long long* __restrict__ tile_state,
+                                                      long long* __restrict__ total) {
     const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
     int x = a + b;
 #pragma unroll
@@ -364,10 +328,53 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
     if (lane == 0) {
       __threadfence();
       atomicExch(&tile_state[tile], FLAG_INC | (unsigned long long)(prefix + tile_total));
-      s_prefix = prefix;
+      *s_prefix = prefix;
       if (tile == n_tiles - 1) *total = prefix + tile_total;
     }
+}
+
+__global__ void __launch_bounds__(kS2Threads)
+stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K, const float* __restrict__ zlut,
+              int32_t* __restrict__ count, int32_t* __restrict__ offset, int32_t* __restrict__ cell_out,
+              int32_t* __restrict__ ray_out, float* __restrict__ z_out, float* __restrict__ zp_out,
+              long long* __restrict__ total, unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
+              int n_tiles) {
+  __shared__ uint32_t s_sel[kS2Rays][4];
+  __shared__ int s_cnt[kS2Rays];
+  __shared__ int s_off[kS2Rays];
+  __shared__ long long s_prefix;
+  __shared__ int s_tile;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_tile = int(atomicAdd(ticket, 1u));
+  __syncthreads();
+  const int tile = s_tile;
+  const long long ray0 = (long long)tile * kS2Rays;
+
+  // phase 1: selection (the warp's 8 row loads are issued up front: 8 x 512 B in flight per warp)
+  float4 rows8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long r = ray0 + warp * 8 + i;
+    rows8[i] = (r < n_rays) ? __ldg(reinterpret_cast<const float4*>(raw0 + r * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = warp * 8 + i;
+    const long long r = ray0 + rl;
+    int cnt = 0;
+    uint32_t sel[4] = {0, 0, 0, 0};
+    if (r < n_rays) cnt = select_cells(rows8[i], thr, K, lane, sel);
+    if (lane == 0) {
+      s_cnt[rl] = cnt;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_sel[rl][j] = sel[j];
+    }
+  }
+  __syncthreads();
+
+  // CTA scan + decoupled look-back (warp 0)
+  if (warp == 0) s2_tile_scan_lookback(s_cnt, s_off, &s_prefix, tile, n_tiles, lane, tile_state, total);
   __syncthreads();
   const long long prefix = s_prefix;
 
@@ -407,6 +414,173 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
   }
 }
 
+// ---- thread-per-ray variant (K <= 16): the default path.
+// The warp-per-ray kernel above spends ~480 warp instructions per ray once most rays overflow K (cross-lane pop rounds),
+// which makes it issue bound at ~15 % of HBM.  Here every THREAD owns a ray, so each instruction advances 32 rays:
+//   * the tile's 64 rows land in shared memory through 64 bulk async copies (one per thread, one mbarrier); rows are
+//     padded to 33 x 16 B so that "thread t reads chunk c of row t" is bank-conflict free,
+//   * a ray is 16 groups of 8 cells; the thread keeps the 16 group maxima (shared memory, 5 x 16 B per thread) and
+//     runs up to K rounds of: max group (first on ties) -> first cell of that group holding the max -> record it,
+//     overwrite it with -inf, refresh the group's maximum.  Round 0 is always taken (the arg-max fallback of
+//     :748-749), later rounds only while the popped value is >= thr, so one loop covers "none", "<= K" and "> K"
+//     survivors with the reference's order (value descending, ties lower cell first) and no per-case branches,
+//   * picks are emitted in ascending cell order (rank = popcount of the selection mask below the cell) into a
+//     shared staging area that aliases the dead rows, then copied out coalesced after the tile's look-back scan.
+constexpr int kS2tRowBytes = 528;
+constexpr int kS2tGmBytes = 80;
+constexpr size_t kS2tSmemBytes = size_t(kS2Rays) * (kS2tRowBytes + kS2tGmBytes) + 128 * sizeof(float);
+
+template <int KMAX>
+__global__ void __launch_bounds__(kS2Rays)
+stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K, const float* __restrict__ zlut,
+                     int32_t* __restrict__ count, int32_t* __restrict__ offset, int32_t* __restrict__ cell_out,
+                     int32_t* __restrict__ ray_out, float* __restrict__ z_out, float* __restrict__ zp_out,
+                     long long* __restrict__ total, unsigned long long* __restrict__ tile_state,
+                     unsigned int* __restrict__ ticket, int n_tiles) {
+  extern __shared__ __align__(16) uint8_t s2t_smem[];
+  uint8_t* rows = s2t_smem;
+  uint8_t* gms = rows + kS2Rays * kS2tRowBytes;
+  float* zl = reinterpret_cast<float*>(gms + kS2Rays * kS2tGmBytes);
+  __shared__ int s_cnt[kS2Rays];
+  __shared__ int s_off[kS2Rays];
+  __shared__ long long s_prefix;
+  __shared__ int s_tile;
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    const int t = int(atomicAdd(ticket, 1u));
+    s_tile = t;
+    const long long left = n_rays - (long long)t * kS2Rays;
+    const uint32_t nv = uint32_t(left < kS2Rays ? left : kS2Rays);
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&s_bar, nv * 512u);
+  }
+  __syncthreads();
+  const int tile = s_tile;
+  const long long ray0 = (long long)tile * kS2Rays;
+  const long long r = ray0 + tid;
+  const bool valid = r < n_rays;
+  uint8_t* row = rows + tid * kS2tRowBytes;
+  if (valid) bulk_g2s(row, raw0 + r * 128, 512u, &s_bar);
+  zl[tid] = zlut[tid];
+  zl[tid + 64] = zlut[tid + 64];
+  mbar_wait(&s_bar, 0, nullptr, 20);
+
+  const float NEG = __int_as_float(0xff800000);
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  float4* gm4 = reinterpret_cast<float4*>(gms + tid * kS2tGmBytes);
+  float* gm = reinterpret_cast<float*>(gm4);
+  auto max8 = [](const float4 a, const float4 b) {
+    return fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+  };
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 g;
+    g.x = max8(row4[8 * q + 0], row4[8 * q + 1]);
+    g.y = max8(row4[8 * q + 2], row4[8 * q + 3]);
+    g.z = max8(row4[8 * q + 4], row4[8 * q + 5]);
+    g.w = max8(row4[8 * q + 6], row4[8 * q + 7]);
+    gm4[q] = g;
+  }
+
+  uint32_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;   // selection mask over the 128 cells
+  float mv[KMAX];                                 // popped values, pick order
+  uint32_t cp[KMAX / 4];                          // popped cells, 8 bits each
+#pragma unroll
+  for (int j = 0; j < KMAX / 4; ++j) cp[j] = 0;
+  int cnt = 0;
+  bool active = valid;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    mv[j] = 0.0f;
+    if (j >= K) break;                                        // warp uniform
+    if (!__any_sync(0xffffffffu, active)) break;              // warp uniform
+    float g[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = gm4[q];
+      g[4 * q + 0] = t.x;
+      g[4 * q + 1] = t.y;
+      g[4 * q + 2] = t.z;
+      g[4 * q + 3] = t.w;
+    }
+    const float m = fmaxf(fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]))),
+                          fmaxf(fmaxf(fmaxf(g[8], g[9]), fmaxf(g[10], g[11])), fmaxf(fmaxf(g[12], g[13]), fmaxf(g[14], g[15]))));
+    int gi = 0;
+#pragma unroll
+    for (int i = 15; i >= 0; --i) gi = (g[i] == m) ? i : gi;   // first group holding the maximum
+    float* grp = reinterpret_cast<float*>(row) + 8 * gi;
+    const float4 a = reinterpret_cast<const float4*>(grp)[0], b = reinterpret_cast<const float4*>(grp)[1];
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    bool found = false;
+    int idx = 0;
+    float nm = NEG;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool e = (x[i] == m) && !found;    // first cell of the group holding the maximum
+      found = found || e;
+      idx = e ? i : idx;
+      nm = fmaxf(nm, e ? NEG : x[i]);          // the group's maximum once that cell is gone
+    }
+    grp[idx] = NEG;
+    gm[gi] = nm;
+    const bool sel = active && (j == 0 || m >= thr);
+    active = sel;
+    const int cell = 8 * gi + idx;
+    const uint32_t bit = sel ? (1u << (cell & 31)) : 0u;
+    const int w = cell >> 5;
+    mk0 |= (w == 0) ? bit : 0u;
+    mk1 |= (w == 1) ? bit : 0u;
+    mk2 |= (w == 2) ? bit : 0u;
+    mk3 |= (w == 3) ? bit : 0u;
+    mv[j] = m;
+    cp[j >> 2] |= uint32_t(cell) << (8 * (j & 3));
+    cnt += sel ? 1 : 0;
+  }
+
+  s_cnt[tid] = cnt;
+  __syncthreads();   // every thread is done with its row: the row area becomes the staging area
+  if (warp == 0) s2_tile_scan_lookback(s_cnt, s_off, &s_prefix, tile, n_tiles, lane, tile_state, total);
+  __syncthreads();
+  const long long prefix = s_prefix;
+  const int off = s_off[tid];
+
+  float* st_z = reinterpret_cast<float*>(rows);
+  float* st_zp = st_z + kS2Rays * KMAX;
+  int32_t* st_ray = reinterpret_cast<int32_t*>(st_zp + kS2Rays * KMAX);
+  int32_t* st_cell = st_ray + kS2Rays * KMAX;
+  const int c0 = __popc(mk0), c1 = c0 + __popc(mk1), c2 = c1 + __popc(mk2);
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j < cnt) {
+      const int cell = int((cp[j >> 2] >> (8 * (j & 3))) & 127u);
+      const int w = cell >> 5;
+      const uint32_t mk = (w == 0) ? mk0 : (w == 1) ? mk1 : (w == 2) ? mk2 : mk3;
+      const int base = (w == 0) ? 0 : (w == 1) ? c0 : (w == 2) ? c1 : c2;
+      const int p = off + base + __popc(mk & ((1u << (cell & 31)) - 1u));
+      st_z[p] = zl[cell];
+      st_zp[p] = mv[j];
+      st_ray[p] = int32_t(r);
+      st_cell[p] = cell;
+    }
+  }
+  if (valid) {
+    count[r] = cnt;
+    offset[r] = int32_t(prefix + off);
+  }
+  __syncthreads();
+  const int tile_total = s_off[kS2Rays - 1] + s_cnt[kS2Rays - 1];
+  for (int i = tid; i < tile_total; i += kS2Rays) {
+    const long long o = prefix + i;
+    z_out[o] = st_z[i];
+    zp_out[o] = st_zp[i];
+    ray_out[o] = st_ray[i];
+    if (cell_out) cell_out[o] = st_cell[i];
+  }
+}
+
 size_t stage2_scratch_bytes(long long n_rays) {
   const long long n_tiles = (n_rays + kS2Rays - 1) / kS2Rays;
   return size_t(n_tiles + 2) * 8;
@@ -421,7 +595,16 @@ cudaError_t launch_stage2(const float* d_raw0, long long n_rays, float thr, int 
   if (e != cudaSuccess) return e;
   unsigned long long* state = reinterpret_cast<unsigned long long*>(d_scratch);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(state + n_tiles);
-  stage2_kernel<<<n_tiles, kS2Threads, 0, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray, d_z, d_zp,
+  // thread-per-ray kernel whenever its assumptions hold (K <= 16, 16-byte aligned rows for the bulk copies)
+  const bool aligned = (reinterpret_cast<uintptr_t>(d_raw0) & 15u) == 0;
+  if (K <= 8 && aligned)
+    stage2_thread_kernel<8><<<n_tiles, kS2Rays, kS2tSmemBytes, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray,
+                                                                   d_z, d_zp, d_total, state, ticket, n_tiles);
+  else if (K <= 16 && aligned)
+    stage2_thread_kernel<16><<<n_tiles, kS2Rays, kS2tSmemBytes, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray,
+                                                                    d_z, d_zp, d_total, state, ticket, n_tiles);
+  else
+    stage2_kernel<<<n_tiles, kS2Threads, 0, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray, d_z, d_zp,
                                                d_total, state, ticket, n_tiles);
   return cudaGetLastError();
 }
