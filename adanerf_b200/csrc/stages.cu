@@ -277,60 +277,75 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
   return v;
 }
 
-// Exclusive scan of the tile's 64 per-ray counts (-> s_off) and decoupled look-back over the preceding tiles
-// (-> *s_prefix); executed by one full warp.  Tiles are numbered by dynamic tickets, so every predecessor a tile
-// spins on has already started.
-__device__ __forceinline__ void s2_tile_scan_lookback(const int* s_cnt, int* s_off, long long* s_prefix, int tile, int n_tiles,
-                                                      int lane, unsigned long long* __restrict__ tile_state,
-                                                      long long* __restrict__ total) {
-    const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
-    int x = a + b;
+// Tile bookkeeping, executed by one full warp.  Tiles are numbered by dynamic tickets, so every predecessor a tile
+// spins on has already started.  A tile's state word carries flag and value together (no fence needed).
+constexpr unsigned long long kS2FlagAgg = 1ull << 62, kS2FlagInc = 2ull << 62, kS2ValMask = (1ull << 62) - 1;
+
+// Exclusive scan of the tile's 64 per-ray counts (-> s_off); publishes the tile aggregate right away so that the
+// successors' look-backs can pass over this tile while it is still busy.  Returns the tile total.
+__device__ __forceinline__ int s2_tile_scan(const int* s_cnt, int* s_off, int tile, int lane,
+                                            unsigned long long* __restrict__ tile_state) {
+  const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+  int x = a + b;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    const int excl = x - (a + b);
-    s_off[2 * lane] = excl;
-    s_off[2 * lane + 1] = excl + a;
-    const int tile_total = __shfl_sync(0xffffffffu, x, 31);
-    const unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
-    long long prefix = 0;
-    if (tile > 0) {
-      if (lane == 0) {
-        atomicExch(&tile_state[tile], FLAG_AGG | (unsigned long long)tile_total);
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  const int excl = x - (a + b);
+  s_off[2 * lane] = excl;
+  s_off[2 * lane + 1] = excl + a;
+  const int tile_total = __shfl_sync(0xffffffffu, x, 31);
+  if (tile > 0 && lane == 0) atomicExch(&tile_state[tile], kS2FlagAgg | (unsigned long long)tile_total);
+  return tile_total;
+}
+
+// Decoupled look-back over the preceding tiles (-> *s_prefix), then publishes this tile's inclusive prefix.
+// The inclusive prefixes travel along the tile sequence one window per L2 round trip, and with ~10^4 small tiles
+// that chain is the kernel's critical path: the window is 128 tiles (4 independent loads per lane in flight) so
+// the chain is ~80 hops instead of ~320.
+__device__ __forceinline__ void s2_lookback(long long* s_prefix, int tile, int tile_total, int n_tiles, int lane,
+                                            unsigned long long* __restrict__ tile_state, long long* __restrict__ total) {
+  long long prefix = 0;
+  if (tile > 0) {
+    int idx = tile - 1;   // nearest predecessor not yet accounted for
+    const long long t0 = clock64();
+    bool done = false;
+    while (!done) {
+      unsigned long long st[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int my = idx - 32 * k - lane;
+        st[k] = (my >= 0) ? ld_volatile_u64(&tile_state[my]) : kS2FlagInc;   // virtual predecessor of tile 0: prefix 0
       }
-      int idx = tile - 1;
-      const long long t0 = clock64();
-      while (true) {
-        const int my = idx - lane;
-        unsigned long long st = FLAG_INC;  // virtual predecessor of tile 0: inclusive prefix 0
-        if (my >= 0) {
-          st = ld_volatile_u64(&tile_state[my]);
-        }
-        const uint32_t ready = __ballot_sync(0xffffffffu, (st >> 62) != 0);
-        const uint32_t inc = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-        // lanes [0, first_inc] must all be ready
-        const int first_inc = inc ? (__ffs(inc) - 1) : 32;
-        const uint32_t need = (first_inc >= 31) ? 0xffffffffu : ((2u << first_inc) - 1u);
-        if ((ready & need) != need) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (done) break;
+        int first_inc;
+        while (true) {
+          const uint32_t ready = __ballot_sync(0xffffffffu, (st[k] >> 62) != 0);
+          const uint32_t inc = __ballot_sync(0xffffffffu, (st[k] >> 62) == 2);
+          first_inc = inc ? (__ffs(inc) - 1) : 32;   // lanes [0, first_inc] must all be ready
+          const uint32_t need = (first_inc >= 31) ? 0xffffffffu : ((2u << first_inc) - 1u);
+          if ((ready & need) == need) break;
           if (clock64() - t0 > ADN_WATCHDOG_CYCLES) asm volatile("trap;");
-          continue;  // spin
+          const int my = idx - 32 * k - lane;
+          if (my >= 0) st[k] = ld_volatile_u64(&tile_state[my]);
         }
-        long long contrib = (lane <= first_inc) ? (long long)(st & VMASK) : 0;
+        long long contrib = (lane <= first_inc) ? (long long)(st[k] & kS2ValMask) : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
         prefix += contrib;
-        if (first_inc < 32) break;
-        idx -= 32;
+        if (first_inc < 32) done = true;
       }
+      idx -= 128;
     }
-    if (lane == 0) {
-      __threadfence();
-      atomicExch(&tile_state[tile], FLAG_INC | (unsigned long long)(prefix + tile_total));
-      *s_prefix = prefix;
-      if (tile == n_tiles - 1) *total = prefix + tile_total;
-    }
+  }
+  if (lane == 0) {
+    atomicExch(&tile_state[tile], kS2FlagInc | (unsigned long long)(prefix + tile_total));
+    *s_prefix = prefix;
+    if (tile == n_tiles - 1) *total = prefix + tile_total;
+  }
 }
 
 __global__ void __launch_bounds__(kS2Threads)
@@ -374,7 +389,10 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
   __syncthreads();
 
   // CTA scan + decoupled look-back (warp 0)
-  if (warp == 0) s2_tile_scan_lookback(s_cnt, s_off, &s_prefix, tile, n_tiles, lane, tile_state, total);
+  if (warp == 0) {
+    const int tile_total = s2_tile_scan(s_cnt, s_off, tile, lane, tile_state);
+    s2_lookback(&s_prefix, tile, tile_total, n_tiles, lane, tile_state, total);
+  }
   __syncthreads();
   const long long prefix = s_prefix;
 
@@ -417,8 +435,8 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
 // ---- thread-per-ray variant (K <= 16): the default path.
 // The warp-per-ray kernel above spends ~480 warp instructions per ray once most rays overflow K (cross-lane pop rounds),
 // which makes it issue bound at ~15 % of HBM.  Here every THREAD owns a ray, so each instruction advances 32 rays:
-//   * the tile's 64 rows land in shared memory through 64 bulk async copies (one per thread, one mbarrier); rows are
-//     padded to 33 x 16 B so that "thread t reads chunk c of row t" is bank-conflict free,
+//   * the tile's 64 rows land in shared memory through cp.async (each warp fetches its own 32 rows, 512 B per
+//     instruction); rows are padded to 33 x 16 B so that "thread t reads chunk c of row t" is bank-conflict free,
 //   * a ray is 16 groups of 8 cells; the thread keeps the 16 group maxima (shared memory, 5 x 16 B per thread) and
 //     runs up to K rounds of: max group (first on ties) -> first cell of that group holding the max -> record it,
 //     overwrite it with -inf, refresh the group's maximum.  Round 0 is always taken (the arg-max fallback of
@@ -445,28 +463,33 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
   __shared__ int s_off[kS2Rays];
   __shared__ long long s_prefix;
   __shared__ int s_tile;
-  __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    const int t = int(atomicAdd(ticket, 1u));
-    s_tile = t;
-    const long long left = n_rays - (long long)t * kS2Rays;
-    const uint32_t nv = uint32_t(left < kS2Rays ? left : kS2Rays);
-    mbar_init(&s_bar, 1);
-    mbar_fence_init();
-    mbar_arrive_expect_tx(&s_bar, nv * 512u);
-  }
+  if (tid == 0) s_tile = int(atomicAdd(ticket, 1u));
   __syncthreads();
   const int tile = s_tile;
   const long long ray0 = (long long)tile * kS2Rays;
   const long long r = ray0 + tid;
   const bool valid = r < n_rays;
   uint8_t* row = rows + tid * kS2tRowBytes;
-  if (valid) bulk_g2s(row, raw0 + r * 128, 512u, &s_bar);
+  // each warp fetches the 32 rows its own threads own: one 512-byte row per cp.async instruction (16 B per lane,
+  // coalesced), nothing staged in registers, and only a __syncwarp between the copies and their consumers.
+  // (A bulk copy per thread serialises into a 32-iteration uniform-register waterfall.)
+  {
+    const float* src = raw0 + (ray0 + warp * 32) * 128 + lane * 4;
+    const uint32_t dst = smem_u32(rows + (warp * 32) * kS2tRowBytes + lane * 16);
+    const long long left = n_rays - (ray0 + warp * 32);
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      if (i < left)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * kS2tRowBytes), "l"(src + i * 128) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   zl[tid] = zlut[tid];
   zl[tid + 64] = zlut[tid + 64];
-  mbar_wait(&s_bar, 0, nullptr, 20);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 
   const float NEG = __int_as_float(0xff800000);
   const float4* row4 = reinterpret_cast<const float4*>(row);
@@ -542,9 +565,9 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
 
   s_cnt[tid] = cnt;
   __syncthreads();   // every thread is done with its row: the row area becomes the staging area
-  if (warp == 0) s2_tile_scan_lookback(s_cnt, s_off, &s_prefix, tile, n_tiles, lane, tile_state, total);
+  int tile_total_w0 = 0;
+  if (warp == 0) tile_total_w0 = s2_tile_scan(s_cnt, s_off, tile, lane, tile_state);
   __syncthreads();
-  const long long prefix = s_prefix;
   const int off = s_off[tid];
 
   float* st_z = reinterpret_cast<float*>(rows);
@@ -566,11 +589,14 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
       st_cell[p] = cell;
     }
   }
+  // the look-back (a chain of L2 round trips) starts only after this warp's own staging work is out of the way
+  if (warp == 0) s2_lookback(&s_prefix, tile, tile_total_w0, n_tiles, lane, tile_state, total);
+  __syncthreads();
+  const long long prefix = s_prefix;
   if (valid) {
     count[r] = cnt;
     offset[r] = int32_t(prefix + off);
   }
-  __syncthreads();
   const int tile_total = s_off[kS2Rays - 1] + s_cnt[kS2Rays - 1];
   for (int i = tid; i < tile_total; i += kS2Rays) {
     const long long o = prefix + i;

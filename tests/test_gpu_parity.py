@@ -143,7 +143,7 @@ def test_stage2_stress_vectors(bare):
     g = load_golden("stage2_stress")
     raw0 = torch.from_numpy(g["raw0"])
     dr = g["meta"]["depth_range"]
-    for K in (1, 4, 8, 16, 128):
+    for K in (1, 4, 8, 16, 32, 64, 128):   # <= 16: thread-per-ray kernel, above: warp-per-ray kernel, 128: dense
         for thr in (0.2, 0.5):
             s2 = bare.stage2(raw0.cuda(), thr, K)
             o2 = orc.stage2_sample(raw0, thr, K, dr)
