@@ -26,6 +26,11 @@ class TensorDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("rows", C.c_int64), ("cols", C.c_int64)]
 
 
+class AuxOutputs(C.Structure):   # adn_aux_outputs: device pointers, any may be NULL
+    _fields_ = [("d_weights", C.c_void_p), ("d_alpha", C.c_void_p), ("d_z_vals", C.c_void_p), ("d_depth_map", C.c_void_p),
+                ("d_acc_map", C.c_void_p), ("d_disp_map", C.c_void_p), ("d_depth_est", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int64), ("ms_stage", C.c_float * 6),
                 ("kernel_launches", C.c_int64)]
@@ -34,7 +39,7 @@ class Stats(C.Structure):
 # every symbol include/adanerf_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     "adn_create", "adn_destroy", "adn_strerror", "adn_last_error", "adn_version", "adn_set_weights",
-    "adn_create_from_export_dir", "adn_probe_export_dir", "adn_set_option", "adn_get_stats", "adn_render_rays", "adn_render_camera",
+    "adn_create_from_export_dir", "adn_probe_export_dir", "adn_set_option", "adn_get_stats", "adn_render_rays", "adn_render_rays_aux", "adn_render_camera",
     "adn_render_camera_rgba8", "adn_render_rays_host", "adn_render_camera_host", "adn_stage0_features",
     "adn_generate_ray_directions", "adn_mlp0_forward", "adn_stage2_sample", "adn_stage3_encode",
     "adn_mlp1_forward", "adn_stage5_composite",
@@ -68,6 +73,7 @@ def load_library():
     lib.adn_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.adn_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.adn_render_rays.argtypes = [vp, fp, fp, f32p, i64, C.c_float, C.c_int, f32p, i32p, f32p, vp]
+    lib.adn_render_rays_aux.argtypes = [vp, fp, fp, f32p, i64, C.c_float, C.c_int, f32p, i32p, f32p, C.POINTER(AuxOutputs), vp]
     lib.adn_render_camera.argtypes = [vp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, f32p, i32p, vp]
     lib.adn_render_camera_rgba8.argtypes = [vp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     lib.adn_render_rays_host.argtypes = [vp, fp, fp, f32p, i64, C.c_float, C.c_int, f32p, i32p]

@@ -19,17 +19,22 @@ from .renderer import Renderer
 KEY_POSE, KEY_ROT, KEY_DIRS = "ImagePose", "ImageRotation", "RayDirectionsSamples"
 KEY_POST, KEY_NET_OUT = "PostProcessedNetworkOutput", "NetworkOutputBatch"
 KEY_ASP, KEY_ORACLE = "AdaptiveSamplePositions", "OracleWeights"
+# FeatureSetKeyConstants (src/features.py:20-40) of the auxiliary tensors RayMarchFromPoses.postprocess stores
+KEY_WEIGHTS, KEY_ALPHA, KEY_ZVALS, KEY_DEPTH = "NeRFWeightsOutput", "NeRFAlphaOutput", "NeRFInputFeatureZVals", "NeRFOutputDepth"
 
 
 class B200Inference:
     """scene: dict (view_cell_center, view_cell_size, depth_range [warped], max_depth, fov) -- the fields
     FeatureSet.initialize reads from DatasetInfo (src/features.py:343-360, :747-767)."""
 
-    def __init__(self, scene, sampling_net, shading_net, threshold, num_samples, device=0, want_oracle_weights=None):
+    def __init__(self, scene, sampling_net, shading_net, threshold, num_samples, device=0, want_oracle_weights=None,
+                 want_aux=False):
         self.renderer = Renderer(scene, device=device, sampling_net=sampling_net, shading_net=shading_net)
         self.threshold = float(threshold)
         self.K = int(num_samples)
         self.want_oracle_weights = (self.threshold == 0.0) if want_oracle_weights is None else bool(want_oracle_weights)
+        # plots.render_all_imgs / the depth export read NeRFWeightsOutput, NeRFAlphaOutput, NeRFOutputDepth (src/plots.py:272-306)
+        self.want_aux = bool(want_aux)
 
     @classmethod
     def from_train_config(cls, train_config, device=0):
@@ -49,7 +54,8 @@ class B200Inference:
         if pose.shape[0] != 1:
             raise ValueError("one image per inference call (evaluate.py / plots.py batch a single image)")
         out = self.renderer.render_rays(pose[0], rot[0], dirs.reshape(-1, 3), self.threshold, self.K,
-                                        want_nsamples=True, want_oracle_weights=self.want_oracle_weights)
+                                        want_nsamples=True, want_oracle_weights=self.want_oracle_weights,
+                                        want_aux=("weights", "alpha", "z_vals", "depth_est") if self.want_aux else False)
         rgb = out["rgb"]
         raw0 = out["oracle_weights"]
         d0 = {KEY_POST: raw0, KEY_NET_OUT: raw0}
@@ -58,6 +64,9 @@ class B200Inference:
             d1[KEY_ASP] = out["n_samples"].to(torch.float32) / self.K
         if raw0 is not None:
             d1[KEY_ORACLE] = raw0
+        if self.want_aux:
+            d1[KEY_WEIGHTS], d1[KEY_ALPHA], d1[KEY_ZVALS] = out["weights"], out["alpha"], out["z_vals"]
+            d1[KEY_DEPTH] = out["depth_est"].reshape(-1, 1)   # features.py:576-577
         return [raw0, rgb], [d0, d1]
 
     __call__ = inference

@@ -464,8 +464,8 @@ adn_status run_mlp(adn_ctx* ctx, int id, const uint8_t* tiles, float* out, const
 
 // The whole hot path for one chunk of rays, stream ordered, no host synchronisation.
 adn_status render_chunk(adn_ctx* ctx, const PoseDev& pd, const float* d_dirs, const CameraRays* cam, int64_t n, float thr,
-                        int K, float* d_rgb, uint8_t* d_rgba8, int32_t* d_nsamples, float* d_oracle_w, cudaStream_t st,
-                        bool timing) {
+                        int K, float* d_rgb, uint8_t* d_rgba8, int32_t* d_nsamples, float* d_oracle_w, const Stage5Aux& aux,
+                        cudaStream_t st, bool timing) {
   const bool dense = (thr == 0.0f);
   const int64_t cap = n * K;
   adn_status s;
@@ -529,7 +529,7 @@ adn_status render_chunk(adn_ctx* ctx, const PoseDev& pd, const float* d_dirs, co
   if (timing) cudaEventRecord(ctx->ev[5], st);
   // stage 5
   ADN_CUDA(ctx, launch_stage5(raw1, dense ? raw0 : static_cast<float*>(ctx->zpbuf.p), static_cast<float*>(ctx->zbuf.p),
-                              ctx->d_zlut_dense, offset, count, n, K, dense ? 1 : 0, d_rgb, d_rgba8, nullptr, nullptr, st));
+                              ctx->d_zlut_dense, offset, count, n, K, dense ? 1 : 0, d_rgb, d_rgba8, aux, st));
   ctx->stats.kernel_launches++;
   if (timing) cudaEventRecord(ctx->ev[6], st);
   return ADN_OK;
@@ -537,7 +537,7 @@ adn_status render_chunk(adn_ctx* ctx, const PoseDev& pd, const float* d_dirs, co
 
 adn_status render_impl(adn_ctx* ctx, const float* pose, const float* rot, const float* d_dirs, const CameraRays* cam,
                        int64_t n_rays, float thr, int K, float* d_rgb, uint8_t* d_rgba8, int32_t* d_nsamples,
-                       float* d_oracle_w, cudaStream_t st) {
+                       float* d_oracle_w, cudaStream_t st, const adn_aux_outputs* ax = nullptr) {
   if (!ctx || !pose || !rot || n_rays < 0 || (!d_rgb && !d_rgba8)) return fail(ctx, ADN_ERR_INVALID, "render: bad arguments");
   if (!ctx->net[0].ready || !ctx->net[1].ready) return fail(ctx, ADN_ERR_NO_WEIGHTS, "render: set both networks first");
   if (ctx->net[0].n_in != 90 || ctx->net[0].n_out != 128) return fail(ctx, ADN_ERR_INVALID, "render: sampling net must be 90 -> 128");
@@ -563,9 +563,21 @@ adn_status render_impl(adn_ctx* ctx, const float* pose, const float* rot, const 
       c = *cam;
       c.row0 = cam->row0 + int(r0 / cam->W);
     }
+    Stage5Aux aux;
+    if (ax) {   // this chunk's window of the caller's per-ray / per-slot buffers
+      aux.weights = ax->d_weights ? ax->d_weights + r0 * K : nullptr;
+      aux.alpha = ax->d_alpha ? ax->d_alpha + r0 * K : nullptr;
+      aux.z_vals = ax->d_z_vals ? ax->d_z_vals + r0 * K : nullptr;
+      aux.depth_map = ax->d_depth_map ? ax->d_depth_map + r0 : nullptr;
+      aux.acc_map = ax->d_acc_map ? ax->d_acc_map + r0 : nullptr;
+      aux.disp_map = ax->d_disp_map ? ax->d_disp_map + r0 : nullptr;
+      aux.depth_est = ax->d_depth_est ? ax->d_depth_est + r0 : nullptr;
+      aux.dr_min = ctx->scene.depth_range[0];
+      aux.log_range = float(std::log(double(ctx->scene.depth_range[1]) - double(ctx->scene.depth_range[0]) + 1.0));
+    }
     s = render_chunk(ctx, pd, d_dirs ? d_dirs + 3 * r0 : nullptr, cam ? &c : nullptr, n, thr, K, d_rgb ? d_rgb + 3 * r0 : nullptr,
                      d_rgba8 ? d_rgba8 + 4 * r0 : nullptr, d_nsamples ? d_nsamples + r0 : nullptr,
-                     d_oracle_w ? d_oracle_w + 128 * r0 : nullptr, st, ctx->profile && r0 == 0);
+                     d_oracle_w ? d_oracle_w + 128 * r0 : nullptr, aux, st, ctx->profile && r0 == 0);
     if (s != ADN_OK) return s;
   }
   return ADN_OK;
@@ -754,6 +766,15 @@ adn_status adn_render_rays(adn_ctx* ctx, const float* pose, const float* rot, co
                      static_cast<cudaStream_t>(stream));
 }
 
+adn_status adn_render_rays_aux(adn_ctx* ctx, const float* pose, const float* rot, const float* d_dirs, int64_t n_rays, float thr,
+                               int K, float* d_rgb, int32_t* d_nsamples, float* d_oracle_weights, const adn_aux_outputs* aux,
+                               void* stream) {
+  if (ctx && n_rays == 0) return ADN_OK;
+  if (!d_dirs) return fail(ctx, ADN_ERR_INVALID, "render_rays_aux: d_dirs is null");
+  return render_impl(ctx, pose, rot, d_dirs, nullptr, n_rays, thr, K, d_rgb, nullptr, d_nsamples, d_oracle_weights,
+                     static_cast<cudaStream_t>(stream), aux);
+}
+
 adn_status adn_render_camera(adn_ctx* ctx, const float* pose, const float* rot, int W, int H, int row0, int rows, float thr,
                              int K, float* d_rgb, int32_t* d_nsamples, void* stream) {
   if (!ctx || W < 1 || H < 1 || row0 < 0 || rows < 0 || row0 + rows > H) return fail(ctx, ADN_ERR_INVALID, "render_camera: bad image window");
@@ -923,8 +944,11 @@ adn_status adn_stage5_composite(adn_ctx* ctx, const float* d_raw1, const float* 
   if (!ctx || !d_raw1 || !d_zp || !d_offset || !d_count || !d_rgb || n_rays < 0 || K < 1 || K > 128 || (d_depth_map && !d_z))
     return fail(ctx, ADN_ERR_INVALID, "stage5: bad arguments");
   ADN_CUDA(ctx, cudaSetDevice(ctx->device));
-  ADN_CUDA(ctx, launch_stage5(d_raw1, d_zp, d_z, nullptr, d_offset, d_count, n_rays, K, 0, d_rgb, nullptr, d_weights,
-                              d_depth_map, static_cast<cudaStream_t>(stream)));
+  Stage5Aux aux;
+  aux.weights = d_weights;
+  aux.depth_map = d_depth_map;
+  ADN_CUDA(ctx, launch_stage5(d_raw1, d_zp, d_z, nullptr, d_offset, d_count, n_rays, K, 0, d_rgb, nullptr, aux,
+                              static_cast<cudaStream_t>(stream)));
   ctx->stats.kernel_launches++;
   return ADN_OK;
 }

@@ -758,17 +758,30 @@ __device__ __forceinline__ uint32_t to_rgba8(float r, float g, float b) {
   return R | (G << 8) | (B << 16) | (255u << 24);
 }
 
+// Per-ray epilogue shared by both composite kernels: acc / disparity / log-warped depth (src/nerf_raymarch_common.py:137-139,
+// src/util/depth_transformations.py:15-35).
+__device__ __forceinline__ void s5_write_ray_aux(const Stage5Aux& aux, long long r, float dm, float acc) {
+  if (aux.depth_map) aux.depth_map[r] = dm;
+  if (aux.acc_map) aux.acc_map[r] = acc;
+  if (aux.disp_map) aux.disp_map[r] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(dm, acc)));
+  if (aux.depth_est) {
+    float d = __fsub_rn(dm, aux.dr_min);
+    if (d <= 0.0f) d = 0.001f;
+    aux.depth_est[r] = __fdiv_rn(logf(__fadd_rn(d, 1.0f)), aux.log_range);
+  }
+}
+
 // One thread per ray, samples visited in order: the same sequential cumprod / sum order as torch.
 __global__ void __launch_bounds__(128)
 stage5_thread_kernel(const float4* __restrict__ raw1, const float* __restrict__ zp, const float* __restrict__ z,
                      const int32_t* __restrict__ offset, const int32_t* __restrict__ count, long long n_rays, int K,
-                     float* __restrict__ rgb, uint32_t* __restrict__ rgba8, float* __restrict__ weights,
-                     float* __restrict__ depth_map) {
+                     float* __restrict__ rgb, uint32_t* __restrict__ rgba8, const Stage5Aux aux) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (r >= n_rays) return;
   const long long off = offset[r];
   const int n = count[r];
-  float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, dm = 0.0f;
+  const bool want_z = aux.depth_map || aux.disp_map || aux.depth_est || aux.z_vals;
+  float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, dm = 0.0f, acc = 0.0f;
   for (int j = 0; j < n; ++j) {
     const float4 q = __ldg(raw1 + off + j);
     const float sr = sigmoidf_acc(q.x), sg = sigmoidf_acc(q.y), sb = sigmoidf_acc(q.z), sa = sigmoidf_acc(q.w);
@@ -778,18 +791,27 @@ stage5_thread_kernel(const float4* __restrict__ raw1, const float* __restrict__ 
     cr = __fadd_rn(cr, __fmul_rn(w, sr));                                         // :135
     cg = __fadd_rn(cg, __fmul_rn(w, sg));
     cb = __fadd_rn(cb, __fmul_rn(w, sb));
-    if (depth_map) dm = __fadd_rn(dm, __fmul_rn(w, __ldg(z + off + j)));          // :137
-    if (weights) weights[r * K + j] = w;
+    acc = __fadd_rn(acc, w);                                                      // :139
+    if (want_z) {
+      const float zz = __ldg(z + off + j);
+      dm = __fadd_rn(dm, __fmul_rn(w, zz));                                       // :137
+      if (aux.z_vals) aux.z_vals[r * K + j] = zz;
+    }
+    if (aux.weights) aux.weights[r * K + j] = w;
+    if (aux.alpha) aux.alpha[r * K + j] = alpha;
   }
-  if (weights)
-    for (int j = n; j < K; ++j) weights[r * K + j] = 0.0f;
+  for (int j = n; j < K; ++j) {
+    if (aux.weights) aux.weights[r * K + j] = 0.0f;
+    if (aux.alpha) aux.alpha[r * K + j] = 0.0f;
+    if (aux.z_vals) aux.z_vals[r * K + j] = __int_as_float(0x7fc00000);          // features.py:546 (NaN padding)
+  }
   if (rgb) {
     rgb[3 * r + 0] = cr;
     rgb[3 * r + 1] = cg;
     rgb[3 * r + 2] = cb;
   }
   if (rgba8) rgba8[r] = to_rgba8(cr, cg, cb);
-  if (depth_map) depth_map[r] = dm;
+  s5_write_ray_aux(aux, r, dm, acc);
 }
 
 // One warp per ray (dense 128 samples / large K): lanes own consecutive samples, transmittance by a
@@ -798,13 +820,14 @@ __global__ void __launch_bounds__(256)
 stage5_warp_kernel(const float4* __restrict__ raw1, const float* __restrict__ zp, const float* __restrict__ z,
                    const float* __restrict__ zlut_dense, const int32_t* __restrict__ offset,
                    const int32_t* __restrict__ count, long long n_rays, int K, int dense, float* __restrict__ rgb,
-                   uint32_t* __restrict__ rgba8, float* __restrict__ weights, float* __restrict__ depth_map) {
+                   uint32_t* __restrict__ rgba8, const Stage5Aux aux) {
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= n_rays) return;
   const long long off = dense ? r * K : (long long)offset[r];
   const int n = dense ? K : count[r];
-  float carry = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, dm = 0.0f;
+  const bool want_z = aux.depth_map || aux.disp_map || aux.depth_est || aux.z_vals;
+  float carry = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, dm = 0.0f, acc = 0.0f;
   for (int j0 = 0; j0 < n; j0 += 32) {
     const int j = j0 + lane;
     float alpha = 0.0f, sr = 0.0f, sg = 0.0f, sb = 0.0f, zz = 0.0f;
@@ -814,7 +837,7 @@ stage5_warp_kernel(const float4* __restrict__ raw1, const float* __restrict__ zp
       sg = sigmoidf_acc(q.y);
       sb = sigmoidf_acc(q.z);
       alpha = __fmul_rn(sigmoidf_acc(q.w), __ldg(zp + off + j));
-      if (depth_map) zz = dense ? __ldg(zlut_dense + j) : __ldg(z + off + j);
+      if (want_z) zz = dense ? __ldg(zlut_dense + j) : __ldg(z + off + j);
     }
     float f = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
     // inclusive product scan
@@ -833,16 +856,26 @@ stage5_warp_kernel(const float4* __restrict__ raw1, const float* __restrict__ zp
     cg = __fadd_rn(cg, __fmul_rn(w, sg));
     cb = __fadd_rn(cb, __fmul_rn(w, sb));
     dm = __fadd_rn(dm, __fmul_rn(w, zz));
-    if (weights && j < K) weights[r * K + j] = (j < n) ? w : 0.0f;
+    acc = __fadd_rn(acc, w);
+    if (j < K) {
+      const bool live = j < n;
+      if (aux.weights) aux.weights[r * K + j] = live ? w : 0.0f;
+      if (aux.alpha) aux.alpha[r * K + j] = live ? alpha : 0.0f;
+      if (aux.z_vals) aux.z_vals[r * K + j] = live ? zz : __int_as_float(0x7fc00000);
+    }
   }
-  if (weights)
-    for (int j = ((n + 31) & ~31) + lane; j < K; j += 32) weights[r * K + j] = 0.0f;
+  for (int j = ((n + 31) & ~31) + lane; j < K; j += 32) {
+    if (aux.weights) aux.weights[r * K + j] = 0.0f;
+    if (aux.alpha) aux.alpha[r * K + j] = 0.0f;
+    if (aux.z_vals) aux.z_vals[r * K + j] = __int_as_float(0x7fc00000);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cr += __shfl_xor_sync(0xffffffffu, cr, o);
     cg += __shfl_xor_sync(0xffffffffu, cg, o);
     cb += __shfl_xor_sync(0xffffffffu, cb, o);
     dm += __shfl_xor_sync(0xffffffffu, dm, o);
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
   }
   if (lane == 0) {
     if (rgb) {
@@ -851,23 +884,23 @@ stage5_warp_kernel(const float4* __restrict__ raw1, const float* __restrict__ zp
       rgb[3 * r + 2] = cb;
     }
     if (rgba8) rgba8[r] = to_rgba8(cr, cg, cb);
-    if (depth_map) depth_map[r] = dm;
+    s5_write_ray_aux(aux, r, dm, acc);
   }
 }
 
 cudaError_t launch_stage5(const float* d_raw1, const float* d_zp, const float* d_z, const float* d_zlut_dense,
                           const int32_t* d_offset, const int32_t* d_count, long long n_rays, int K, int dense, float* d_rgb,
-                          uint8_t* d_rgba8, float* d_weights, float* d_depth_map, cudaStream_t s) {
+                          uint8_t* d_rgba8, const Stage5Aux& aux, cudaStream_t s) {
   if (n_rays <= 0) return cudaSuccess;
   const float4* raw = reinterpret_cast<const float4*>(d_raw1);
   uint32_t* rgba = reinterpret_cast<uint32_t*>(d_rgba8);
   if (dense || K > 32) {
     const long long threads = n_rays * 32;
     stage5_warp_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(raw, d_zp, d_z, d_zlut_dense, d_offset, d_count, n_rays,
-                                                                        K, dense, d_rgb, rgba, d_weights, d_depth_map);
+                                                                        K, dense, d_rgb, rgba, aux);
   } else {
     stage5_thread_kernel<<<unsigned((n_rays + 127) / 128), 128, 0, s>>>(raw, d_zp, d_z, d_offset, d_count, n_rays, K, d_rgb,
-                                                                         rgba, d_weights, d_depth_map);
+                                                                         rgba, aux);
   }
   return cudaGetLastError();
 }

@@ -45,9 +45,24 @@ cudaError_t launch_stage3(const SceneDev& sc, const float* d_ray_o, const float*
                           const float* d_z, const float* d_zlut_dense, int K, long long n_samples, const long long* d_total,
                           float* d_x1, uint8_t* d_tiles1, cudaStream_t s);
 
+// Optional per-ray / per-slot outputs of the composite (adaptive_raw2outputs' other return values and the tensors
+// RayMarchFromPoses.postprocess puts into the inference dict, src/features.py:536-577).  Any pointer may be null.
+struct Stage5Aux {
+  float* weights = nullptr;     // [N,K] zero padded (NeRFWeightsOutput)
+  float* alpha = nullptr;       // [N,K] zero padded, sigmoid(a) * zp (NeRFAlphaOutput)
+  float* z_vals = nullptr;      // [N,K] world depth, NaN padded (NeRFInputFeatureZVals)
+  float* depth_map = nullptr;   // [N] sum w z
+  float* acc_map = nullptr;     // [N] sum w
+  float* disp_map = nullptr;    // [N] 1 / max(1e-10, depth_map / acc_map)
+  float* depth_est = nullptr;   // [N] LogTransform.from_world(depth_map, depth_range) (NeRFOutputDepth)
+  float dr_min = 0.0f;          // depth_range[0]
+  float log_range = 1.0f;       // float(log(depth_range[1] - depth_range[0] + 1))
+  bool any() const { return weights || alpha || z_vals || depth_map || acc_map || disp_map || depth_est; }
+};
+
 // Stage 5.  zp: adaptive -> packed [M]; dense (dense_zp_stride > 0) -> raw0 [N, stride].
 cudaError_t launch_stage5(const float* d_raw1, const float* d_zp, const float* d_z, const float* d_zlut_dense,
                           const int32_t* d_offset, const int32_t* d_count, long long n_rays, int K, int dense,
-                          float* d_rgb, uint8_t* d_rgba8, float* d_weights, float* d_depth_map, cudaStream_t s);
+                          float* d_rgb, uint8_t* d_rgba8, const Stage5Aux& aux, cudaStream_t s);
 
 }  // namespace adn

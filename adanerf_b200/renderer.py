@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import AdnError, Scene, Stats, TensorDesc
+from ._lib import AdnError, AuxOutputs, Scene, Stats, TensorDesc
 
 
 def make_scene(view_cell_center, view_cell_size, depth_range, max_depth, fov, z_near=0.001, z_far=1.0,
@@ -116,19 +116,38 @@ class Renderer:
         return t if t.is_contiguous() else t.contiguous()
 
     # ---- the hot path --------------------------------------------------------------------
-    def render_rays(self, pose, rot, dirs, thr, K, want_nsamples=True, want_oracle_weights=False):
-        """dirs [N,3] (cuda tensor) -> dict(rgb [N,3], n_samples [N] int32, oracle_weights [N,128])."""
+    AUX_KEYS = ("weights", "alpha", "z_vals", "depth_map", "acc_map", "disp_map", "depth_est")
+
+    def render_rays(self, pose, rot, dirs, thr, K, want_nsamples=True, want_oracle_weights=False, want_aux=False):
+        """dirs [N,3] (cuda tensor) -> dict(rgb [N,3], n_samples [N] int32, oracle_weights [N,128]).
+        want_aux: True or an iterable of AUX_KEYS -> additionally weights / alpha / z_vals [N,K] and depth_map /
+        acc_map / disp_map / depth_est [N] (adaptive_raw2outputs' other outputs, src/nerf_raymarch_common.py:137-144;
+        depth_est = "NeRFOutputDepth", src/features.py:574-577)."""
         p, r = self._pose_rot(pose, rot)
         d = self._f32(dirs).reshape(-1, 3)
         n = d.shape[0]
         rgb = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
         ns = torch.empty((n,), dtype=torch.int32, device=self._dev()) if want_nsamples else None
         ow = torch.empty((n, 128), dtype=torch.float32, device=self._dev()) if want_oracle_weights else None
+        out = dict(rgb=rgb, n_samples=ns, oracle_weights=ow)
         with torch.cuda.device(self.device):
-            self._check(self.lib.adn_render_rays(self.handle, _fptr(p), _fptr(r), d.data_ptr(), n, float(thr), int(K),
-                                                 rgb.data_ptr(), ns.data_ptr() if ns is not None else None,
-                                                 ow.data_ptr() if ow is not None else None, self._stream()))
-        return dict(rgb=rgb, n_samples=ns, oracle_weights=ow)
+            if want_aux:
+                keys = self.AUX_KEYS if want_aux is True else tuple(want_aux)
+                aux = AuxOutputs()
+                for k in keys:
+                    if k not in self.AUX_KEYS:
+                        raise KeyError(f"unknown auxiliary output {k!r}")
+                    t = torch.empty((n, int(K)) if k in ("weights", "alpha", "z_vals") else (n,), dtype=torch.float32, device=self._dev())
+                    out[k] = t
+                    setattr(aux, "d_" + k, t.data_ptr())
+                self._check(self.lib.adn_render_rays_aux(self.handle, _fptr(p), _fptr(r), d.data_ptr(), n, float(thr), int(K),
+                                                         rgb.data_ptr(), ns.data_ptr() if ns is not None else None,
+                                                         ow.data_ptr() if ow is not None else None, C.byref(aux), self._stream()))
+            else:
+                self._check(self.lib.adn_render_rays(self.handle, _fptr(p), _fptr(r), d.data_ptr(), n, float(thr), int(K),
+                                                     rgb.data_ptr(), ns.data_ptr() if ns is not None else None,
+                                                     ow.data_ptr() if ow is not None else None, self._stream()))
+        return out
 
     def render_camera(self, pose, rot, W, H, thr, K, row0=0, rows=None, out=None, want_nsamples=False):
         """Renders image rows [row0, row0+rows) of a WxH pinhole frame; rays generated on the device."""

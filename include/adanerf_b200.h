@@ -109,6 +109,23 @@ adn_status adn_render_rays(adn_ctx* ctx, const float* pose, const float* rot, co
                            float thr, int K, float* d_rgb, int32_t* d_nsamples, float* d_oracle_weights,
                            void* stream);
 
+/* Auxiliary outputs of the same call: the other return values of adaptive_raw2outputs
+ * (src/nerf_raymarch_common.py:137-144) and the tensors RayMarchFromPoses.postprocess stores in the inference dict
+ * (src/features.py:536-577), read by plots.render_all_imgs / the depth export (src/plots.py:272-306).
+ * Every pointer is a device pointer and may be NULL; [N,K] tensors are padded like the reference's. */
+typedef struct adn_aux_outputs {
+  float* d_weights;    /* [N,K] "NeRFWeightsOutput": alpha * transmittance, 0 in unused slots */
+  float* d_alpha;      /* [N,K] "NeRFAlphaOutput": sigmoid(raw alpha) * sampling-net value, 0 in unused slots */
+  float* d_z_vals;     /* [N,K] "NeRFInputFeatureZVals": world depth of the samples, NaN in unused slots */
+  float* d_depth_map;  /* [N] sum_k w z (world depth) */
+  float* d_acc_map;    /* [N] sum_k w */
+  float* d_disp_map;   /* [N] 1 / max(1e-10, depth_map / acc_map) */
+  float* d_depth_est;  /* [N] "NeRFOutputDepth": LogTransform.from_world(depth_map, depth_range) */
+} adn_aux_outputs;
+adn_status adn_render_rays_aux(adn_ctx* ctx, const float* pose, const float* rot, const float* d_dirs, int64_t n_rays,
+                               float thr, int K, float* d_rgb, int32_t* d_nsamples, float* d_oracle_weights,
+                               const adn_aux_outputs* aux, void* stream);
+
 /* Same, generating the pinhole rays of image rows [row0, row0+rows) of a WxH frame on the device
  * (src/util/raygeneration.py:10-26; ray id = y*W + x).  Replaces Camera::UpdateFeaturesBatch +
  * ImageGenerator::inference's batch loop (camera.cpp:160-201, imagegenerator.cpp:247-478).

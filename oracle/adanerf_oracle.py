@@ -233,7 +233,17 @@ def stage5_composite(raw1, z_packed, zp, mapping, n_rays, K):
     rgb = torch.sum(weights[..., None] * restored[..., :3], -2)            # :135
     depth_map = torch.sum(weights * restored_z, -1)           # :137
     acc = torch.sum(weights, -1)                              # :139
-    return dict(rgb=rgb, weights=weights, alpha=alpha, depth_map=depth_map, acc=acc)
+    disp = 1.0 / torch.max(1e-10 * torch.ones_like(depth_map), depth_map / acc)   # :138
+    return dict(rgb=rgb, weights=weights, alpha=alpha, depth_map=depth_map, acc=acc, disp=disp)
+
+
+def log_from_world(depth, depth_range):
+    """LogTransform.from_world -- src/util/depth_transformations.py:15-35 (torch branch), on a copy."""
+    min_d, max_d = depth_range[0], depth_range[1]
+    max_v = max_d - min_d
+    d = depth.clone() - min_d
+    d[d <= 0] = 0.001
+    return torch.log(d + 1.0) / math.log(max_v + 1)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -260,7 +270,8 @@ def render_rays(pose, rot, dirs, sd0, sd1, scene, thr, K, return_stages=False):
     if return_stages:
         out.update(x0=x0, ray_o=ray_o, ray_d=ray_d, raw0=raw0, z=s2["z"], zp=s2["zp"], cell=s2["cell"],
                    count=s2["count"], x1=x1, mapping=mapping, z_packed=zs, raw1=raw1,
-                   weights=comp["weights"], alpha=comp["alpha"], depth_map=comp["depth_map"], acc=comp["acc"])
+                   weights=comp["weights"], alpha=comp["alpha"], depth_map=comp["depth_map"], acc=comp["acc"],
+                   disp=comp["disp"], depth_est=log_from_world(comp["depth_map"], scene["depth_range"]))   # features.py:576-577
     return out
 
 

@@ -50,7 +50,7 @@ def stage_case(name, scene_name, scene, sd0, sd1, K, thr, n_rays, stride, pose_o
     arrays = dict(meta=meta(case=name, scene=scene_name, K=K, thr=thr, w=w, h=h, scene_params=scene),
                   pix=pix.numpy().astype(np.int64), dirs=dirs.numpy(), pose=pose.numpy(), rot=rot.numpy(),
                   x0=st["x0"], raw0=st["raw0"], ray_o=st["ray_o"], ray_d=st["ray_d"], rgb=st["rgb"],
-                  weights=st["weights"], alpha=st["alpha"])
+                  weights=st["weights"], alpha=st["alpha"], depth_est=st["depth_est"])
     if thr > 0:
         z = st["z_nan"]
         arrays.update(z_nan=z, asp=st["asp"], raw1_pad=st["raw1_pad"])

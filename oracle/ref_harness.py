@@ -117,6 +117,7 @@ class RefRenderer:
             x0=d0[F.input_feature_batch], raw0=d0[F.network_output],
             ray_o=d0[F.input_feature_ray_origins], ray_d=d0[F.input_feature_ray_directions],
             rgb=outs[1], weights=d1[F.nerf_weights_output], alpha=d1[F.nerf_alpha_output],
+            depth_est=d1[F.nerf_estimated_depth],                 # [N,1] LogTransform.from_world(depth_map)
         )
         if F.adaptive_sample_positions in d1:
             res["asp"] = d1[F.adaptive_sample_positions]

@@ -49,3 +49,19 @@ def test_inference_adapter_dense_returns_oracle_weights():
     ow = dicts[1]["OracleWeights"].cpu().numpy()
     np.testing.assert_allclose(ow, g["raw0"], rtol=0, atol=2e-4 * np.abs(g["raw0"]).max())
     assert "AdaptiveSamplePositions" not in dicts[1]
+
+
+def test_inference_adapter_auxiliary_dict_entries():
+    """want_aux=True: the keys plots.render_all_imgs / the depth export read (src/plots.py:272-306)."""
+    g = load_golden("pav_k8_t0.2")
+    m = g["meta"]
+    sd0, sd1 = case_weights("pav_k8_t0.2")
+    inf = B200Inference(m["scene_params"], sd0, sd1, m["thr"], m["K"], want_aux=True)
+    outs, dicts = inf.inference(_Batch(g))
+    d1 = dicts[1]
+    n, K = g["dirs"].shape[0], m["K"]
+    assert d1["NeRFWeightsOutput"].shape == (n, K) and d1["NeRFAlphaOutput"].shape == (n, K)
+    assert d1["NeRFInputFeatureZVals"].shape == (n, K) and d1["NeRFOutputDepth"].shape == (n, 1)
+    same = np.round(d1["AdaptiveSamplePositions"].cpu().numpy() * K) == np.round(g["asp"] * K)
+    np.testing.assert_allclose(d1["NeRFOutputDepth"].cpu().numpy()[same], g["depth_est"][same], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(d1["NeRFWeightsOutput"].cpu().numpy()[same], g["weights"][same], rtol=0, atol=2e-2)

@@ -288,6 +288,67 @@ def test_render_matches_reference(case):
     r.close()
 
 
+@pytest.mark.parametrize("case", ["pav_k8_t0.2", "pav_k8_t0.5", "shaped_k8_t0.2"])
+def test_render_auxiliary_outputs(case):
+    """adn_render_rays_aux: weights / alpha / z_vals [N,K], depth / acc / disparity / NeRFOutputDepth [N] against the
+    reference's inference dict (golden) and against the oracle on the same per-sample values."""
+    g = load_golden(case)
+    m = g["meta"]
+    K = m["K"]
+    sd0, sd1 = case_weights(case)
+    r = _renderer(m["scene_params"], sd0, sd1)
+    dirs = torch.from_numpy(g["dirs"]).cuda()
+    out = r.render_rays(g["pose"], g["rot"], dirs, m["thr"], K, want_aux=True)
+    plain = r.render_rays(g["pose"], g["rot"], dirs, m["thr"], K)
+    assert torch.equal(out["rgb"], plain["rgb"])                     # asking for more does not change the image
+    ns = out["n_samples"].cpu().numpy()
+    same = (ns == np.round(g["asp"] * K).astype(np.int32))
+    assert same.mean() >= 0.98
+    w, a, z = (out[k].cpu().numpy() for k in ("weights", "alpha", "z_vals"))
+    # padding exactly like the reference's: zeros / NaN behind the ray's samples
+    slot = np.arange(K)[None, :] >= ns[:, None]
+    assert (w[slot] == 0).all() and (a[slot] == 0).all() and np.isnan(z[slot]).all() and np.isfinite(z[~slot]).all()
+    np.testing.assert_allclose(z[same], g["z_nan"][same], rtol=3e-7, atol=0, equal_nan=True)
+    # bf16 shading net: compare like the image (SURVEY 8d), weights / alpha live in [0, 1] for trained / shaped nets
+    np.testing.assert_allclose(w[same], g["weights"][same], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(a[same], g["alpha"][same], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(out["depth_est"].cpu().numpy()[same], g["depth_est"][same, 0], rtol=0, atol=2e-2)
+    # internal consistency, exact up to summation order: acc = sum w, depth = sum w z, disparity, log warp
+    wt, zt = out["weights"].double(), torch.nan_to_num(out["z_vals"], nan=0.0).double()
+    acc, dm = wt.sum(1), (wt * zt).sum(1)
+    np.testing.assert_allclose(out["acc_map"].cpu().numpy(), acc.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["depth_map"].cpu().numpy(), dm.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["disp_map"].cpu().numpy(),
+                               (1.0 / torch.clamp(out["depth_map"] / out["acc_map"], min=1e-10)).cpu().numpy(), rtol=1e-5)
+    de = orc.log_from_world(out["depth_map"].cpu(), m["scene_params"]["depth_range"]).numpy()
+    np.testing.assert_allclose(out["depth_est"].cpu().numpy(), de, rtol=0, atol=2e-6)
+    only = r.render_rays(g["pose"], g["rot"], dirs, m["thr"], K, want_aux=("depth_est",))
+    assert torch.equal(only["depth_est"], out["depth_est"]) and "weights" not in only
+    r.close()
+
+
+def test_render_auxiliary_outputs_chunked_and_dense():
+    """Aux buffers are windowed per internal chunk; dense mode (K = 128) goes through the warp-per-ray composite."""
+    scene = orc.SCENE_BARBERSHOP
+    sd0, sd1 = orc.make_weights("shaped", seed=0)
+    r = _renderer(scene, sd0, sd1)
+    pose, rot = torch.tensor(scene["view_cell_center"]), torch.eye(3)
+    dirs = torch.from_numpy(orc.generate_ray_directions(800, 800, scene["fov"]).reshape(-1, 3)).float()[::97][:6000].cuda()
+    one = r.render_rays(pose, rot, dirs, 0.2, 8, want_aux=True)
+    r.set_option("chunk_rays", 1024)
+    many = r.render_rays(pose, rot, dirs, 0.2, 8, want_aux=True)
+    r.set_option("chunk_rays", 0)
+    for k in ("rgb",) + r.AUX_KEYS:
+        assert torch.equal(torch.nan_to_num(one[k], nan=-1.0), torch.nan_to_num(many[k], nan=-1.0)), k
+    d = r.render_rays(pose, rot, dirs[:512], 0.0, 128, want_aux=True)
+    ref = orc.render_rays(pose, rot, dirs[:512].cpu(), sd0, sd1, scene, 0.0, 128, return_stages=True)
+    assert torch.isfinite(d["z_vals"]).all()
+    np.testing.assert_allclose(d["z_vals"].cpu().numpy(), ref["z"].numpy(), rtol=3e-7)
+    np.testing.assert_allclose(d["weights"].cpu().numpy(), ref["weights"].numpy(), rtol=0, atol=2e-2)
+    np.testing.assert_allclose(d["acc_map"].cpu().numpy(), ref["acc"].numpy(), rtol=0, atol=5e-2)
+    r.close()
+
+
 def test_render_dense_config1():
     """BASELINE config 1: first 1024 rays of the 800x800 grid, dense 128 samples, random init."""
     g = load_golden("rand_dense_k128")

@@ -54,6 +54,29 @@ def test_end_to_end_matches_reference(case):
     assert orc.psnr(o["rgb"].numpy()[same], g["rgb"][same]) > 60.0
 
 
+@pytest.mark.parametrize("case", ["pav_k8_t0.2", "pav_k8_t0.5", "shaped_k8_t0.2"])
+def test_auxiliary_outputs_match_reference(case):
+    """NeRFWeightsOutput / NeRFAlphaOutput / NeRFOutputDepth of the reference's inference dict (features.py:566-577)
+    on the rays whose sample set the host's GEMM rounding did not change."""
+    g, m, o = _run(case)
+    same = (o["asp"].numpy() == g["asp"])
+    assert same.mean() > 0.98
+    np.testing.assert_allclose(o["weights"].numpy()[same], g["weights"][same], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(o["alpha"].numpy()[same], g["alpha"][same], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(o["depth_est"].numpy()[same], g["depth_est"][same, 0], rtol=0, atol=2e-3)
+    # and exactly, given the reference's own per-sample network output: composite + log warp are elementwise fp32
+    K, n = m["K"], g["weights"].shape[0]
+    mapping = torch.from_numpy(np.isfinite(g["z_nan"]).reshape(-1))
+    raw1 = torch.from_numpy(g["raw1_pad"].reshape(-1, 4))[mapping]
+    zs = torch.from_numpy(g["z_nan"].reshape(-1))[mapping]
+    s2 = orc.stage2_sample(torch.from_numpy(g["raw0"]), m["thr"], K, m["scene_params"]["depth_range"])
+    comp = orc.stage5_composite(raw1, zs, s2["zp"], mapping, n, K)
+    np.testing.assert_allclose(comp["weights"].numpy(), g["weights"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(comp["alpha"].numpy(), g["alpha"], rtol=0, atol=1e-6)
+    de = orc.log_from_world(comp["depth_map"], m["scene_params"]["depth_range"]).numpy()
+    np.testing.assert_allclose(de, g["depth_est"][:, 0], rtol=0, atol=1e-6)
+
+
 def test_dense_config1_matches_reference():
     """BASELINE config 1: 1024 rays, dense 128 samples, random init (chunked like evaluate.py:216-235)."""
     g = load_golden("rand_dense_k128")
