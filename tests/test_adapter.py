@@ -56,8 +56,12 @@ def test_inference_adapter_auxiliary_dict_entries():
     g = load_golden("pav_k8_t0.2")
     m = g["meta"]
     sd0, sd1 = case_weights("pav_k8_t0.2")
+    from adanerf_b200.adapter import B200Inference
     inf = B200Inference(m["scene_params"], sd0, sd1, m["thr"], m["K"], want_aux=True)
-    outs, dicts = inf.inference(_Batch(g))
+    batch = _Batch({"ImagePose": torch.from_numpy(g["pose"]).reshape(1, 3).cuda(),
+                    "ImageRotation": torch.from_numpy(g["rot"]).reshape(1, 3, 3).cuda(),
+                    "RayDirectionsSamples": torch.from_numpy(g["dirs"]).reshape(1, -1, 3).cuda()})
+    outs, dicts = inf.inference(batch, gradient=False, is_inference=True)
     d1 = dicts[1]
     n, K = g["dirs"].shape[0], m["K"]
     assert d1["NeRFWeightsOutput"].shape == (n, K) and d1["NeRFAlphaOutput"].shape == (n, K)
