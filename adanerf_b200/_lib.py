@@ -42,7 +42,7 @@ SYMBOLS = [
     "adn_create_from_export_dir", "adn_probe_export_dir", "adn_set_option", "adn_get_stats", "adn_render_rays", "adn_render_rays_aux", "adn_render_camera",
     "adn_render_camera_rgba8", "adn_render_rays_host", "adn_render_camera_host", "adn_stage0_features",
     "adn_generate_ray_directions", "adn_mlp0_forward", "adn_stage2_sample", "adn_stage3_encode",
-    "adn_mlp1_forward", "adn_stage5_composite",
+    "adn_mlp1_forward", "adn_stage5_composite", "adn_image_metrics",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library():
     lib.adn_stage3_encode.argtypes = [vp, f32p, f32p, i32p, f32p, i64, f32p, vp]
     lib.adn_mlp1_forward.argtypes = [vp, f32p, i64, f32p, vp]
     lib.adn_stage5_composite.argtypes = [vp, f32p, f32p, f32p, i32p, i32p, i64, C.c_int, f32p, f32p, f32p, vp]
+    lib.adn_image_metrics.argtypes = [vp, f32p, f32p, i64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("adn_destroy", "adn_strerror", "adn_last_error", "adn_version"):

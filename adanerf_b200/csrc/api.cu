@@ -55,7 +55,7 @@ struct adn_ctx {
   int64_t chunk_rays = 0;
   bool profile = false;
   // scratch
-  Buf tiles0, raw0, x0, ray_o, ray_d, dirs, count, offset, rayidx, zbuf, zpbuf, tiles1, raw1, s2scratch, rgb, rgba, x1;
+  Buf tiles0, raw0, x0, ray_o, ray_d, dirs, count, offset, rayidx, zbuf, zpbuf, tiles1, raw1, s2scratch, rgb, rgba, x1, metric;
   long long* d_total = nullptr;
   int* d_err = nullptr;
   long long* d_trace = nullptr;   // debug timeline of the MLP kernels (option "trace")
@@ -660,7 +660,7 @@ void adn_destroy(adn_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   Buf* bufs[] = {&ctx->tiles0, &ctx->raw0, &ctx->x0,    &ctx->ray_o,  &ctx->ray_d, &ctx->dirs,      &ctx->count, &ctx->offset,
-                 &ctx->rayidx, &ctx->zbuf, &ctx->zpbuf, &ctx->tiles1, &ctx->raw1,  &ctx->s2scratch, &ctx->rgb,   &ctx->rgba, &ctx->x1};
+                 &ctx->rayidx, &ctx->zbuf, &ctx->zpbuf, &ctx->tiles1, &ctx->raw1,  &ctx->s2scratch, &ctx->rgb,   &ctx->rgba, &ctx->x1, &ctx->metric};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& r : ctx->reg)
@@ -950,6 +950,26 @@ adn_status adn_stage5_composite(adn_ctx* ctx, const float* d_raw1, const float* 
   ADN_CUDA(ctx, launch_stage5(d_raw1, d_zp, d_z, nullptr, d_offset, d_count, n_rays, K, 0, d_rgb, nullptr, aux,
                               static_cast<cudaStream_t>(stream)));
   ctx->stats.kernel_launches++;
+  return ADN_OK;
+}
+
+adn_status adn_image_metrics(adn_ctx* ctx, const float* d_image, const float* d_reference, int64_t n_values, int clamp01,
+                             double* mse_out, double* psnr_out, void* stream) {
+  if (!ctx || !d_image || !d_reference || n_values < 1 || (!mse_out && !psnr_out))
+    return fail(ctx, ADN_ERR_INVALID, "image_metrics: bad arguments");
+  ADN_CUDA(ctx, cudaSetDevice(ctx->device));
+  adn_status s = ensure(ctx, ctx->metric, sizeof(double) * (kMetricBlocks + 1));
+  if (s != ADN_OK) return s;
+  double* part = static_cast<double*>(ctx->metric.p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ADN_CUDA(ctx, launch_image_sqdiff(d_image, d_reference, n_values, clamp01, part, part + kMetricBlocks, st));
+  ctx->stats.kernel_launches += 2;
+  double sum = 0.0;
+  ADN_CUDA(ctx, cudaMemcpyAsync(&sum, part + kMetricBlocks, sizeof(double), cudaMemcpyDeviceToHost, st));
+  ADN_CUDA(ctx, cudaStreamSynchronize(st));
+  const double mse = sum / double(n_values);                       // calculate_mse, src/evaluate.py:49-50
+  if (mse_out) *mse_out = mse;
+  if (psnr_out) *psnr_out = 10.0 * std::log10(1.0 / mse);         // calculate_psnr, src/evaluate.py:53-54
   return ADN_OK;
 }
 

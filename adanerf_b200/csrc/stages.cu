@@ -905,4 +905,43 @@ cudaError_t launch_stage5(const float* d_raw1, const float* d_zp, const float* d
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------- metrics
+__global__ void __launch_bounds__(256)
+sqdiff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int clamp01,
+                      double* __restrict__ partials) {
+  __shared__ double s_w[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
+    float x = __ldg(a + i);
+    if (clamp01) x = fminf(fmaxf(x, 0.0f), 1.0f);
+    const double d = double(x) - double(__ldg(b + i));
+    acc += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(32) sqdiff_final_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) acc += partials[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+cudaError_t launch_image_sqdiff(const float* d_a, const float* d_b, long long n_values, int clamp01, double* d_partials,
+                                double* d_sum, cudaStream_t s) {
+  sqdiff_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(d_a, d_b, n_values, clamp01, d_partials);
+  sqdiff_final_kernel<<<1, 32, 0, s>>>(d_partials, kMetricBlocks, d_sum);
+  return cudaGetLastError();
+}
+
 }  // namespace adn

@@ -193,6 +193,17 @@ class Renderer:
         return dict(rgb=rgb, n_samples=ns)
 
     # ---- stage-level entry points (parity tests) --------------------------------------------
+    def image_metrics(self, image, reference, clamp01=False):
+        """MSE / PSNR of two device images (src/evaluate.py:49-54), reduced on the device."""
+        a, b = self._f32(image).reshape(-1), self._f32(reference).reshape(-1)
+        if a.numel() != b.numel():
+            raise ValueError("image_metrics: shapes differ")
+        mse, psnr = C.c_double(), C.c_double()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.adn_image_metrics(self.handle, a.data_ptr(), b.data_ptr(), a.numel(), int(bool(clamp01)),
+                                                   C.byref(mse), C.byref(psnr), self._stream()))
+        return dict(mse=mse.value, psnr=psnr.value)
+
     def generate_ray_directions(self, W, H, row0=0, rows=None):
         rows = H - row0 if rows is None else rows
         out = torch.empty((rows * W, 3), dtype=torch.float32, device=self._dev())

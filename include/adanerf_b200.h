@@ -171,6 +171,13 @@ adn_status adn_stage5_composite(adn_ctx* ctx, const float* d_raw1, const float* 
                                 const int32_t* d_offset, const int32_t* d_count, int64_t n_rays, int K,
                                 float* d_rgb, float* d_weights, float* d_depth_map, void* stream);
 
+/* ---- evaluation metric on the device ------------------------------------------------------ */
+/* calculate_mse / calculate_psnr (src/evaluate.py:49-54) of two device images of n_values floats each:
+ * mse = sum((a - b)^2) / n_values (double accumulation, deterministic), psnr = 10 log10(1 / mse).
+ * clamp01 != 0 clips d_image to [0,1] first (src/evaluate.py:257-258).  Synchronises the stream; results on the host. */
+adn_status adn_image_metrics(adn_ctx* ctx, const float* d_image, const float* d_reference, int64_t n_values, int clamp01,
+                             double* mse_out, double* psnr_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

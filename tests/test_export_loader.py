@@ -80,3 +80,33 @@ def test_render_from_export_dir_matches_state_dict(tmp_path):
     assert torch.equal(a, b)
     r1.close()
     r2.close()
+
+
+def test_weights_checkpoints_to_export_dir(lib, tmp_path):
+    """`.weights` (torch.save(state_dict), src/models.py:87-90) -> export directory -> C++ loader."""
+    import ctypes as C
+    import torch
+    from adanerf_b200 import convert
+    from adanerf_b200._lib import Scene
+    sd0, sd1 = orc.make_weights("rand", seed=5)
+    torch.save(sd0, tmp_path / "Net0_opt.weights")
+    torch.save(sd1, tmp_path / "Net1_opt.weights")
+    scene = orc.SCENE_PAVILLON
+    with open(tmp_path / "dataset_info.txt", "w") as f:
+        for k in ("view_cell_center", "view_cell_size", "depth_range", "fov", "max_depth"):
+            f.write(f"{k} = {scene[k]}\n")
+    out = tmp_path / "export"
+    convert.main(["--weights0", str(tmp_path / "Net0_opt.weights"), "--weights1", str(tmp_path / "Net1_opt.weights"),
+                  "--dataset-info", str(tmp_path / "dataset_info.txt"), "--threshold", "0.15", "--samples", "16", "--out", str(out)])
+    sc, thr, K, nt = Scene(), C.c_float(), C.c_int(), (C.c_int * 2)()
+    assert lib.adn_probe_export_dir(str(out).encode(), C.byref(sc), C.byref(thr), C.byref(K), nt) == 0
+    assert abs(thr.value - 0.15) < 1e-7 and K.value == 16 and list(nt) == [len(sd0), len(sd1)]
+    assert abs(sc.max_depth - scene["max_depth"]) < 1e-6
+    back = ow.read_onnx_initializers(str(out / "model1.onnx"))
+    np.testing.assert_array_equal(back["rgb_linear.weight"], sd1["rgb_linear.weight"].numpy())
+    # wrong architecture is rejected with a message
+    bad = dict(sd1)
+    del bad["views_linears.0.weight"]
+    torch.save(bad, tmp_path / "bad.weights")
+    with pytest.raises(ValueError, match="views_linears"):
+        convert.weights_to_export_dir(tmp_path / "Net0_opt.weights", tmp_path / "bad.weights", tmp_path / "x", scene, 0.2, 8)

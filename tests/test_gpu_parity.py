@@ -464,3 +464,21 @@ def test_render_ragged_sizes(n):
         assert torch.equal(out["n_samples"].cpu().long(), ref["n_samples"])
         assert np.abs(out["rgb"].cpu().numpy() - ref["rgb"].numpy()).max() < 5e-3
     r.close()
+
+
+def test_image_metrics_on_device(bare):
+    """adn_image_metrics == calculate_mse / calculate_psnr (src/evaluate.py:49-54)."""
+    g = torch.Generator().manual_seed(11)
+    a = torch.rand(800 * 800, 3, generator=g) * 1.2 - 0.1
+    b = torch.rand(800 * 800, 3, generator=g)
+    m = bare.image_metrics(a.cuda(), b.cuda())
+    diff = (a.double() - b.double())
+    mse = float(diff.pow(2).sum() / diff.numel())
+    assert abs(m["mse"] - mse) < 1e-12 and abs(m["psnr"] - 10 * np.log10(1.0 / mse)) < 1e-9
+    mc = bare.image_metrics(a.cuda(), b.cuda(), clamp01=True)
+    d2 = a.clamp(0, 1).double() - b.double()
+    assert abs(mc["mse"] - float(d2.pow(2).sum() / d2.numel())) < 1e-12
+    again = bare.image_metrics(a.cuda(), b.cuda())
+    assert again == m                                              # deterministic reduction
+    with pytest.raises(Exception):
+        bare.image_metrics(a.cuda(), b[:10].cuda())
