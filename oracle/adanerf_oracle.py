@@ -41,6 +41,10 @@ SCENE_PAVILLON = dict(
 # ----------------------------------------------------------------------------------------------
 # stage 0a: pixel ray directions -- src/util/raygeneration.py:10-26 (float64 numpy, like the ref)
 # ----------------------------------------------------------------------------------------------
+# the NDC / LLFF variant (configs/fine_training_ndc.ini) on the same geometry: dataset w, h feed ndc_rays (features.py:430)
+SCENE_PAVILLON_NDC = dict(SCENE_PAVILLON, use_ndc=True, w=800, h=800)
+
+
 def generate_ray_directions(w, h, fov, focal=None):
     if focal is None:
         focal = 0.5 * w / math.tan(0.5 * fov)  # src/datasets.py:181-182
@@ -125,9 +129,11 @@ def log_to_world(z, depth_range):
 # ----------------------------------------------------------------------------------------------
 # stage 2: FromClassifiedDepthAdaptive.generate -- src/nerf_raymarch_common.py:699-757
 # ----------------------------------------------------------------------------------------------
-def stage2_sample(raw0, thr, K, depth_range, z_near=0.001, z_far=1.0):
+def stage2_sample(raw0, thr, K, depth_range, z_near=0.001, z_far=1.0, no_depth_range=False):
     """raw0 [N,128] -> dict(z [N,K] world depth (inf padded, ascending), zp [N,K], cell [N,K] int64
-    (-1 padded), count [N] int64).  Dense path (thr == 0): z [N,K] only, zp = raw0 (features.py:504-505)."""
+    (-1 padded), count [N] int64).  Dense path (thr == 0): z [N,K] only, zp = raw0 (features.py:504-505).
+    no_depth_range: FromClassifiedDepthAdaptiveNoDepthRange (nerf_raymarch_common.py:763-854) -- the same
+    selection, z stays the cell centre in [0,1] (no LogTransform.to_world) and the dense z are lerp(z_near, z_far)."""
     n = raw0.shape[0]
     if thr == 0.0:                                            # :708-720
         t_vals = torch.linspace(0.0, 1.0, steps=int(K + 1))[0:-1] + (0.5 / K)
@@ -136,7 +142,7 @@ def stage2_sample(raw0, thr, K, depth_range, z_near=0.001, z_far=1.0):
         far = torch.ones((n, 1), dtype=raw0.dtype) * z_far
         z = near * (1.0 - t_vals) + far * t_vals
         cell = torch.arange(K, dtype=torch.int64)[None, :].expand(n, K)
-        return dict(z=log_to_world(z, depth_range), zp=raw0, cell=cell,
+        return dict(z=z if no_depth_range else log_to_world(z, depth_range), zp=raw0, cell=cell,
                     count=torch.full((n,), K, dtype=torch.int64))
     disc = raw0.shape[1]
     cell_size = 1.0 / disc
@@ -159,7 +165,7 @@ def stage2_sample(raw0, thr, K, depth_range, z_near=0.001, z_far=1.0):
                        torch.full_like(perm, -1))
     n_r = torch.clamp(count, max=K)
     n_r = torch.where(empty, torch.ones_like(n_r), n_r)
-    return dict(z=log_to_world(z, depth_range), zp=zp, cell=cell, count=n_r)
+    return dict(z=z if no_depth_range else log_to_world(z, depth_range), zp=zp, cell=cell, count=n_r)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -172,11 +178,36 @@ def normalize_inverse_sqrt_dist_centered(x, center, max_depth):
     return loc / (math.sqrt(max_depth) * local[..., None])
 
 
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """src/nerf_raymarch_common.py:71-88 (taken from nerf-pytorch), same operation order."""
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    rays_o = rays_o + t[..., None] * rays_d
+    o0 = -1. / (W / (2. * focal)) * rays_o[..., 0] / rays_o[..., 2]
+    o1 = -1. / (H / (2. * focal)) * rays_o[..., 1] / rays_o[..., 2]
+    o2 = 1. + 2. * near / rays_o[..., 2]
+    d0 = -1. / (W / (2. * focal)) * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
+    d1 = -1. / (H / (2. * focal)) * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
+    d2 = -2. * near / rays_o[..., 2]
+    return torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
+
+
+def scene_ndc(scene):
+    """(H, W, focal) of the NDC variant (features.py:350-351,430: dataset h, w and view.focal), or None."""
+    if not scene.get("use_ndc"):
+        return None
+    w, h = int(scene["w"]), int(scene["h"])
+    focal = scene.get("focal") or 0.5 * w / math.tan(0.5 * scene["fov"])   # src/datasets.py:181-182
+    return h, w, float(focal)
+
+
 def stage3_encode(ray_o, ray_d, z, scene, compact=True, n_freq_pos=10, n_freq_dir=4):
     """ray_o, ray_d [N,3]; z [N,K] world depth (inf = dead slot).
     -> x1 [M,90] (pos block FIRST), mapping [N*K] bool, z_packed [M].  The reference encodes all N*K
     slots and then masks (features.py:458-484); restated the same way but dead slots are skipped
-    (their values are discarded by the mask and never observed)."""
+    (their values are discarded by the mask and never observed).
+    NDC variant (scene["use_ndc"], features.py:429-431): rays go through ndc_rays first, the sample positions use the
+    un-normalised NDC direction, the view encoding its normalised copy, and there is no position normalisation
+    (rayMarchNormalization None, nerf_raymarch_common.py:195-196)."""
     dt = ray_o.dtype
     n, k = z.shape
     c = torch.tensor(scene["view_cell_center"], dtype=torch.float32).to(dt)   # features.py:345
@@ -184,8 +215,14 @@ def stage3_encode(ray_o, ray_d, z, scene, compact=True, n_freq_pos=10, n_freq_di
     sel = torch.nonzero(mapping).flatten()
     ray_idx = sel // k
     zs = z.flatten()[sel]
-    pos = ray_o[ray_idx] + ray_d[ray_idx] * zs[:, None]                       # :458
-    pos = normalize_inverse_sqrt_dist_centered(pos, c, scene["max_depth"])    # :466-467
+    ndc = scene_ndc(scene)
+    if ndc is not None:
+        ray_o, rays_d = ndc_rays(ndc[0], ndc[1], ndc[2], 1., ray_o, ray_d)    # :430
+        ray_d = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)              # :431
+        pos = ray_o[ray_idx] + rays_d[ray_idx] * zs[:, None]                   # :458
+    else:
+        pos = ray_o[ray_idx] + ray_d[ray_idx] * zs[:, None]                   # :458
+        pos = normalize_inverse_sqrt_dist_centered(pos, c, scene["max_depth"])    # :466-467
     x1 = torch.cat([posenc(pos, n_freq_pos), posenc(ray_d[ray_idx], n_freq_dir)], -1)   # :473-479
     return x1, mapping, zs
 
@@ -252,9 +289,11 @@ def log_from_world(depth, depth_range):
 def render_rays(pose, rot, dirs, sd0, sd1, scene, thr, K, return_stages=False):
     """One `inference` call of the reference on one batch of rays (all tensors CPU)."""
     with torch.no_grad():
-        x0, ray_o, ray_d = stage0_sphere_pos_dir(pose, rot, dirs, scene)
+        ndc = bool(scene.get("use_ndc"))
+        # sampling-net encoding: posEncArgs[0] = "10-4", or "2-2" in the NDC configs (configs/fine_training_ndc.ini:8)
+        x0, ray_o, ray_d = stage0_sphere_pos_dir(pose, rot, dirs, scene, n_freq_pos=2 if ndc else 10, n_freq_dir=2 if ndc else 4)
         raw0 = mlp0_forward(x0, sd0)
-        s2 = stage2_sample(raw0, thr, K, scene["depth_range"])
+        s2 = stage2_sample(raw0, thr, K, scene["depth_range"], no_depth_range=ndc)
         n = dirs.shape[0]
         if thr == 0.0:
             x1, mapping, zs = stage3_encode(ray_o, ray_d, s2["z"], scene, compact=False)
@@ -271,7 +310,8 @@ def render_rays(pose, rot, dirs, sd0, sd1, scene, thr, K, return_stages=False):
         out.update(x0=x0, ray_o=ray_o, ray_d=ray_d, raw0=raw0, z=s2["z"], zp=s2["zp"], cell=s2["cell"],
                    count=s2["count"], x1=x1, mapping=mapping, z_packed=zs, raw1=raw1,
                    weights=comp["weights"], alpha=comp["alpha"], depth_map=comp["depth_map"], acc=comp["acc"],
-                   disp=comp["disp"], depth_est=log_from_world(comp["depth_map"], scene["depth_range"]))   # features.py:576-577
+                   disp=comp["disp"],   # NeRFOutputDepth: the depth map itself with NDC, else log-warped (features.py:573-577)
+                   depth_est=comp["depth_map"] if ndc else log_from_world(comp["depth_map"], scene["depth_range"]))
     return out
 
 
@@ -340,11 +380,16 @@ def make_weights(kind="shaped", seed=0, thr=0.2, target_spr=8.0):
     'shaped' : same seed, then the sampling net's last layer is scaled by 0.15 and its bias shifted so
                that the mean number of cells >= thr is ~target_spr of 128 on a probe batch, and the
                shading net's last layers are damped so sigmoid inputs look trained (raw0 is used
-               un-squashed, so plain random init saturates every ray at K and drives alpha*zp out of [0,1])."""
+               un-squashed, so plain random init saturates every ray at K and drives alpha*zp out of [0,1]).
+    'ndc'    : sampling net with 30 inputs (configs/fine_training_ndc.ini), last layer damped by a fixed recipe."""
     torch.manual_seed(seed)
-    sd0 = init_sampling_net()
+    sd0 = init_sampling_net(n_in=30 if kind == "ndc" else 90)
     sd1 = init_shading_net()
     if kind == "rand":
+        return sd0, sd1
+    if kind == "ndc":   # NDC configs: posEncArgs[0] = "2-2" -> 30 input features; damped last layer, ragged 12..16 of K = 16
+        sd0["layers.7.weight"] = sd0["layers.7.weight"] * 0.15
+        sd0["layers.7.bias"] = sd0["layers.7.bias"] * 0.15 - 0.1
         return sd0, sd1
     if kind != "shaped":
         raise ValueError(kind)

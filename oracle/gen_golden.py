@@ -38,13 +38,13 @@ def save(name, **arrays):
     print(f"wrote {path}  ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
-def stage_case(name, scene_name, scene, sd0, sd1, K, thr, n_rays, stride, pose_off, rot, keep_x1, w=800, h=800):
+def stage_case(name, scene_name, scene, sd0, sd1, K, thr, n_rays, stride, pose_off, rot, keep_x1, w=800, h=800, ndc=False):
     dirs_all = torch.from_numpy(rh.generate_ray_directions(
         w, h, scene["fov"], 0.5 * w / np.tan(0.5 * scene["fov"])).reshape(-1, 3)).float()
     pix = (torch.arange(n_rays) * stride) % (w * h)
     dirs = dirs_all[pix]
     pose = torch.tensor(scene["view_cell_center"], dtype=torch.float32) + torch.tensor(pose_off, dtype=torch.float32)
-    r = rh.RefRenderer(scene, K=K, thr=thr, w=w, h=h)
+    r = rh.RefRenderer(scene, K=K, thr=thr, w=w, h=h, ndc=ndc)
     r.load_state_dicts(sd0, sd1)
     st = r.stages(pose, rot, dirs)
     arrays = dict(meta=meta(case=name, scene=scene_name, K=K, thr=thr, w=w, h=h, scene_params=scene),
@@ -121,6 +121,10 @@ def main():
     stage_case("rand_k8_t0.2", "barbershop", bar, r0, r1, 8, 0.2, 256, 2503, [0.0, 0.0, 0.0], torch.eye(3), False)
     # BASELINE config 1: first 1024 rays of the 800x800 grid, dense 128 samples/ray, random init
     stage_case("rand_dense_k128", "barbershop", bar, r0, r1, 128, 0.0, 1024, 1, [0.0, 0.0, 0.0], torch.eye(3), False)
+    # NDC / LLFF variant (configs/fine_training_ndc.ini): 30-feature sampling net, NoDepthRange sampler, ndc_rays
+    n0, n1 = orc.make_weights("ndc", seed=0)
+    stage_case("ndc_k16_t0.15", "pavillon_ndc", orc.SCENE_PAVILLON_NDC, n0, n1, 16, 0.15, 256, 2501, [0.1, -0.05, 0.02],
+               orc.rotation_yaw(20.0), True, ndc=True)
     stage2_stress()
 
 

@@ -33,9 +33,13 @@ def _install_stubs():
         sys.path.insert(0, REF_SRC)
 
 
-def make_config(K=8, thr=0.2, pos_enc_args=("10-4", "10-4")):
-    """Namespace with exactly the fields the two FeatureSets/models read (configs/fine_training.ini)."""
-    return Namespace(
+def make_config(K=8, thr=0.2, pos_enc_args=("10-4", "10-4"), ndc=False):
+    """Namespace with exactly the fields the two FeatureSets/models read (configs/fine_training.ini;
+    ndc=True: configs/fine_training_ndc.ini -- posEncArgs [2-2, 10-4], FromClassifiedDepthAdaptiveNoDepthRange,
+    rayMarchNormalization [.., None], depthTransform linear, useNDC)."""
+    if ndc:
+        pos_enc_args = ("2-2", "10-4")
+    cfg = Namespace(
         inFeatures=["SpherePosDir", "RayMarchFromPoses"],
         outFeatures=["RawSigmoid", "RGBARayMarch"],
         posEnc=["nerf", "nerf"], posEncArgs=list(pos_enc_args),
@@ -55,32 +59,38 @@ def make_config(K=8, thr=0.2, pos_enc_args=("10-4", "10-4")):
         lossBlendingStart=0, lossBlendingDuration=1, lossWeights=[0.025, 1.0],
         scale=1,
     )
+    if ndc:
+        cfg.rayMarchSampler = ["none", "FromClassifiedDepthAdaptiveNoDepthRange"]
+        cfg.rayMarchNormalization = ["InverseSqrtDistCentered", "None"]
+        cfg.useNDC = True
+        cfg.depthTransform = "linear"
+    return cfg
 
 
-def make_dataset_info(scene, w, h):
+def make_dataset_info(scene, w, h, ndc=False):
     """Fake DatasetInfo with the attributes FeatureSet.initialize reads (src/datasets.py:146-213)."""
     _install_stubs()
-    from util.depth_transformations import LogTransform
+    from util.depth_transformations import LogTransform, LinearTransform
     view = Namespace(view_cell_center=list(scene["view_cell_center"]),
                      view_cell_size=list(scene["view_cell_size"]),
                      fov=scene["fov"], focal=0.5 * w / math.tan(0.5 * scene["fov"]), camera_scale=1.0)
     return Namespace(view=view, w=w, h=h, depth_max=scene["max_depth"],
                      depth_range=list(scene["depth_range"]),
                      depth_range_warped=list(scene["depth_range"]),
-                     depth_transform=LogTransform, use_warped_depth_range=[True, True])
+                     depth_transform=LinearTransform if ndc else LogTransform, use_warped_depth_range=[True, True])
 
 
 class RefRenderer:
     """Builds f_in/f_out/models exactly as TrainConfig.initialize would and exposes inference()."""
 
-    def __init__(self, scene, K=8, thr=0.2, w=800, h=800, seed=0):
+    def __init__(self, scene, K=8, thr=0.2, w=800, h=800, seed=0, ndc=False):
         _install_stubs()
         torch.manual_seed(seed)
         from features import FeatureSet
         from models import ModelSelection
         from train_data import TrainConfig
-        self.cfg = make_config(K=K, thr=thr)
-        self.dataset_info = make_dataset_info(scene, w, h)
+        self.cfg = make_config(K=K, thr=thr, ndc=ndc)
+        self.dataset_info = make_dataset_info(scene, w, h, ndc=ndc)
         f_in, f_out = FeatureSet.get_sets(self.cfg, "cpu")
         for f in list(f_in) + list(f_out):
             f.initialize(self.cfg, self.dataset_info, "cpu")

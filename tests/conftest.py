@@ -37,6 +37,8 @@ def case_weights(case):
         return load_pavillon_weights()
     if case.startswith("shaped"):
         return orc.make_weights("shaped", seed=0)
+    if case.startswith("ndc"):
+        return orc.make_weights("ndc", seed=0)
     return orc.make_weights("rand", seed=0)
 
 

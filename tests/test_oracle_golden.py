@@ -8,7 +8,7 @@ from conftest import load_golden, case_weights
 from oracle import adanerf_oracle as orc
 from oracle import ref_harness as rh
 
-CASES = ["pav_k8_t0.2", "pav_k8_t0.5", "pav_k16_t0.15", "shaped_k8_t0.2", "rand_k8_t0.2"]
+CASES = ["pav_k8_t0.2", "pav_k8_t0.5", "pav_k16_t0.15", "shaped_k8_t0.2", "rand_k8_t0.2", "ndc_k16_t0.15"]
 
 
 def _run(case):
@@ -34,7 +34,8 @@ def test_stage2_bit_exact_on_reference_raw0(case):
     """Feed the reference's own raw0: counts, cells, order and z must match bit for bit."""
     g = load_golden(case)
     m = g["meta"]
-    s2 = orc.stage2_sample(torch.from_numpy(g["raw0"]), m["thr"], m["K"], m["scene_params"]["depth_range"])
+    s2 = orc.stage2_sample(torch.from_numpy(g["raw0"]), m["thr"], m["K"], m["scene_params"]["depth_range"],
+                           no_depth_range=bool(m["scene_params"].get("use_ndc")))
     z = s2["z"].numpy().copy()
     z[~np.isfinite(z)] = np.nan
     np.testing.assert_array_equal(z, g["z_nan"])
@@ -69,7 +70,8 @@ def test_auxiliary_outputs_match_reference(case):
     mapping = torch.from_numpy(np.isfinite(g["z_nan"]).reshape(-1))
     raw1 = torch.from_numpy(g["raw1_pad"].reshape(-1, 4))[mapping]
     zs = torch.from_numpy(g["z_nan"].reshape(-1))[mapping]
-    s2 = orc.stage2_sample(torch.from_numpy(g["raw0"]), m["thr"], K, m["scene_params"]["depth_range"])
+    s2 = orc.stage2_sample(torch.from_numpy(g["raw0"]), m["thr"], K, m["scene_params"]["depth_range"],
+                           no_depth_range=bool(m["scene_params"].get("use_ndc")))
     comp = orc.stage5_composite(raw1, zs, s2["zp"], mapping, n, K)
     np.testing.assert_allclose(comp["weights"].numpy(), g["weights"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(comp["alpha"].numpy(), g["alpha"], rtol=0, atol=1e-6)
