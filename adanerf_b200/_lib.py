@@ -19,7 +19,9 @@ class AdnError(RuntimeError):
 class Scene(C.Structure):
     _fields_ = [("view_cell_center", C.c_float * 3), ("view_cell_size", C.c_float * 3),
                 ("depth_range", C.c_float * 2), ("max_depth", C.c_float), ("fov", C.c_float),
-                ("z_near", C.c_float), ("z_far", C.c_float), ("n_freq_pos", C.c_int32), ("n_freq_dir", C.c_int32)]
+                ("z_near", C.c_float), ("z_far", C.c_float), ("n_freq_pos", C.c_int32), ("n_freq_dir", C.c_int32),
+                ("n_freq_pos0", C.c_int32), ("n_freq_dir0", C.c_int32),          # sampling-net encoding (0 = same)
+                ("use_ndc", C.c_int32), ("ndc_w", C.c_int32), ("ndc_h", C.c_int32), ("ndc_focal", C.c_float)]
 
 
 class TensorDesc(C.Structure):

@@ -42,8 +42,8 @@ def check_state_dicts(sd0, sd1):
     for k in SHADING_KEYS:
         if k not in sd1:
             raise ValueError(f"shading net: missing {k} (expected NeRF with use_viewdirs, src/models.py:214-250)")
-    if sd0["layers.0.weight"].shape[1] != 90 or sd1["pts_linears.0.weight"].shape[1] != 63:
-        raise ValueError("posEncArgs other than [10-4, 10-4] (90 / 63+27 input features) are not supported")
+    if sd0["layers.0.weight"].shape[1] not in (90, 30) or sd1["pts_linears.0.weight"].shape[1] != 63:
+        raise ValueError("posEncArgs other than [10-4, 10-4] / [2-2, 10-4] (90 or 30 / 63+27 input features) are not supported")
 
 
 def read_dataset_info(path):

@@ -51,6 +51,7 @@ struct adn_ctx {
   int dense_K = 0;
   Net net[2];
   int mlp0_terms = 3;
+  int n_feat0 = 90;               // sampling-net input features: 6 + 6 (n_freq_pos0 + n_freq_dir0)
   int cta_group = 2;              // MLP kernels: 2 = CTA pairs (cta_group::2 MMAs), 1 = single CTA
   int64_t chunk_rays = 0;
   bool profile = false;
@@ -403,6 +404,15 @@ adn_status build_net1(adn_ctx* ctx) {
   return ADN_OK;
 }
 
+// ndc_rays' projection constants -1 / (W / (2 focal)), -1 / (H / (2 focal)): python doubles that are rounded once when
+// they meet the fp32 tensors (src/nerf_raymarch_common.py:77-82).  focal <= 0: 0.5 W / tan(fov / 2) (src/datasets.py:181-182,
+// adanerf_real_time_viewer/src/featureset.cpp:83-84).
+void set_ndc_projection(adn_ctx* ctx, int W, int H, float focal_in) {
+  const double focal = focal_in > 0.0f ? double(focal_in) : 0.5 * double(W) / std::tan(0.5 * double(ctx->scene.fov));
+  ctx->sc.ndc_cw = float(-1.0 / (double(W) / (2.0 * focal)));
+  ctx->sc.ndc_ch = float(-1.0 / (double(H) / (2.0 * focal)));
+}
+
 adn_status ensure_dense_lut(adn_ctx* ctx, int K) {
   if (ctx->dense_K == K && ctx->d_zlut_dense) return ADN_OK;
   // thr == 0 branch of FromClassifiedDepthAdaptive.generate (nerf_raymarch_common.py:708-720), fp32 steps
@@ -415,7 +425,7 @@ adn_status ensure_dense_lut(adn_ctx* ctx, int K) {
     const float t = lin + float(0.5 / K);
     const float z = ctx->scene.z_near * (1.0f - t) + ctx->scene.z_far * t;
     const float w = float(std::pow(max_v + 1.0, double(z)));
-    lut[k] = (w - 1.0f) + ctx->scene.depth_range[0];
+    lut[k] = ctx->scene.use_ndc ? z : (w - 1.0f) + ctx->scene.depth_range[0];   // NoDepthRange: :797-805
   }
   if (ctx->d_zlut_dense) cudaFree(ctx->d_zlut_dense);
   ctx->d_zlut_dense = nullptr;
@@ -500,9 +510,9 @@ adn_status render_chunk(adn_ctx* ctx, const PoseDev& pd, const float* d_dirs, co
     ADN_CUDA(ctx, launch_stage0(ctx->sc, pd, d_dirs, cam, n, nullptr, ray_o, ray_d, tiles0, st));
     ctx->stats.kernel_launches++;
   } else {
-    if ((s = ensure(ctx, ctx->x0, size_t(n) * 90 * 4)) != ADN_OK) return s;
+    if ((s = ensure(ctx, ctx->x0, size_t(n) * ctx->n_feat0 * 4)) != ADN_OK) return s;
     ADN_CUDA(ctx, launch_stage0(ctx->sc, pd, d_dirs, cam, n, static_cast<float*>(ctx->x0.p), ray_o, ray_d, nullptr, st));
-    ADN_CUDA(ctx, launch_pack_rows(static_cast<float*>(ctx->x0.p), n, nullptr, 90, n0.lay, tiles0, st));
+    ADN_CUDA(ctx, launch_pack_rows(static_cast<float*>(ctx->x0.p), n, nullptr, ctx->n_feat0, n0.lay, tiles0, st));
     ctx->stats.kernel_launches += 2;
   }
   if (timing) cudaEventRecord(ctx->ev[1], st);
@@ -540,10 +550,17 @@ adn_status render_impl(adn_ctx* ctx, const float* pose, const float* rot, const 
                        float* d_oracle_w, cudaStream_t st, const adn_aux_outputs* ax = nullptr) {
   if (!ctx || !pose || !rot || n_rays < 0 || (!d_rgb && !d_rgba8)) return fail(ctx, ADN_ERR_INVALID, "render: bad arguments");
   if (!ctx->net[0].ready || !ctx->net[1].ready) return fail(ctx, ADN_ERR_NO_WEIGHTS, "render: set both networks first");
-  if (ctx->net[0].n_in != 90 || ctx->net[0].n_out != 128) return fail(ctx, ADN_ERR_INVALID, "render: sampling net must be 90 -> 128");
+  if (ctx->net[0].n_in != ctx->n_feat0 || ctx->net[0].n_out != 128)
+    return fail(ctx, ADN_ERR_INVALID, "render: sampling net must be " + std::to_string(ctx->n_feat0) + " -> 128 for this scene's encoding");
   if (K < 1 || K > 128 || thr < 0.0f) return fail(ctx, ADN_ERR_INVALID, "render: need 1 <= K <= 128 and thr >= 0");
   if (thr == 0.0f && K != 128) return fail(ctx, ADN_ERR_INVALID, "render: dense mode (thr == 0) needs K == 128 (one sample per depth cell)");
   if (n_rays == 0) return ADN_OK;
+  if (ctx->scene.use_ndc) {
+    // image size behind ndc_rays: the frame being rendered (viewer, featureset.cpp:83-84) or the dataset's (features.py:350-351,430)
+    if (cam) set_ndc_projection(ctx, cam->W, cam->H, 0.0f);
+    else if (ctx->scene.ndc_w > 0 && ctx->scene.ndc_h > 0) set_ndc_projection(ctx, ctx->scene.ndc_w, ctx->scene.ndc_h, ctx->scene.ndc_focal);
+    else return fail(ctx, ADN_ERR_INVALID, "render: NDC scene needs ndc_w / ndc_h when rays are passed explicitly");
+  }
   ADN_CUDA(ctx, cudaSetDevice(ctx->device));
   adn_status s;
   if (thr == 0.0f && (s = ensure_dense_lut(ctx, K)) != ADN_OK) return s;
@@ -572,6 +589,7 @@ adn_status render_impl(adn_ctx* ctx, const float* pose, const float* rot, const 
       aux.acc_map = ax->d_acc_map ? ax->d_acc_map + r0 : nullptr;
       aux.disp_map = ax->d_disp_map ? ax->d_disp_map + r0 : nullptr;
       aux.depth_est = ax->d_depth_est ? ax->d_depth_est + r0 : nullptr;
+      aux.linear_depth = ctx->scene.use_ndc ? 1 : 0;
       aux.dr_min = ctx->scene.depth_range[0];
       aux.log_range = float(std::log(double(ctx->scene.depth_range[1]) - double(ctx->scene.depth_range[0]) + 1.0));
     }
@@ -613,7 +631,11 @@ adn_status adn_create(adn_ctx** out, const adn_scene* scene, int device) {
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ADN_ERR_NO_DEVICE;
   if (prop.major != 10) return ADN_ERR_NO_DEVICE;  // tcgen05 / TMEM kernels: sm_100 family only, no fallback
-  if (scene->n_freq_pos != 10 || scene->n_freq_dir != 4) return ADN_ERR_INVALID;  // posEncArgs "10-4" (F = 90)
+  if (scene->n_freq_pos != 10 || scene->n_freq_dir != 4) return ADN_ERR_INVALID;  // posEncArgs[1] "10-4" (F = 90)
+  const int nfp0 = scene->n_freq_pos0 ? scene->n_freq_pos0 : scene->n_freq_pos;
+  const int nfd0 = scene->n_freq_dir0 ? scene->n_freq_dir0 : scene->n_freq_dir;
+  if (!((nfp0 == 10 && nfd0 == 4) || (nfp0 == 2 && nfd0 == 2))) return ADN_ERR_INVALID;   // posEncArgs[0] "10-4" or "2-2"
+  if (scene->use_ndc && (scene->ndc_w < 0 || scene->ndc_h < 0)) return ADN_ERR_INVALID;
   adn_ctx* ctx = new adn_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
@@ -632,13 +654,19 @@ adn_status adn_create(adn_ctx** out, const adn_scene* scene, int device) {
   ctx->sc.sqrt_max_depth = float(std::sqrt(double(scene->max_depth)));
   ctx->sc.n_freq_pos = scene->n_freq_pos;
   ctx->sc.n_freq_dir = scene->n_freq_dir;
+  ctx->sc.n_freq_pos0 = nfp0;
+  ctx->sc.n_freq_dir0 = nfd0;
+  ctx->n_feat0 = 6 + 6 * (nfp0 + nfd0);
+  ctx->sc.ndc = scene->use_ndc ? 1 : 0;
+  if (scene->use_ndc && scene->ndc_w > 0 && scene->ndc_h > 0) set_ndc_projection(ctx, scene->ndc_w, scene->ndc_h, scene->ndc_focal);
   // z LUT: LogTransform.to_world((cell + .5)/128) (depth_transformations.py:37-48), pow in double, rest in fp32
   float lut[128];
   const double max_v = double(scene->depth_range[1]) - double(scene->depth_range[0]);
   for (int i = 0; i < 128; ++i) {
     const float z = (float(i) + 0.5f) * (1.0f / 128.0f);
     const float w = float(std::pow(max_v + 1.0, double(z)));
-    lut[i] = (w - 1.0f) + scene->depth_range[0];
+    // FromClassifiedDepthAdaptiveNoDepthRange (NDC configs): the cell centre itself (nerf_raymarch_common.py:826-833)
+    lut[i] = scene->use_ndc ? z : (w - 1.0f) + scene->depth_range[0];
   }
   bool ok = cudaMalloc(&ctx->d_zlut, sizeof(lut)) == cudaSuccess &&
             cudaMemcpy(ctx->d_zlut, lut, sizeof(lut), cudaMemcpyHostToDevice) == cudaSuccess &&

@@ -188,14 +188,24 @@ bool load_export_dir(const std::string& dir_in, ExportDir& out, std::string& err
   s.n_freq_dir = 4;
   auto pe = cfg.find("posEncArgs");
   if (pe != cfg.end()) {
-    const auto items = list_items(pe->second);   // "10-4"
-    if (!items.empty()) {
-      const size_t dash = items.back().find('-');
-      if (dash != std::string::npos) {
-        s.n_freq_pos = std::atoi(items.back().substr(0, dash).c_str());
-        s.n_freq_dir = std::atoi(items.back().substr(dash + 1).c_str());
-      }
-    }
+    const auto items = list_items(pe->second);   // [sampling net, shading net], e.g. [10-4, 10-4] or [2-2, 10-4]
+    auto parse = [](const std::string& it, int32_t& pos, int32_t& dir) {
+      const size_t dash = it.find('-');
+      if (dash == std::string::npos) return;
+      pos = std::atoi(it.substr(0, dash).c_str());
+      dir = std::atoi(it.substr(dash + 1).c_str());
+    };
+    if (!items.empty()) parse(items.back(), s.n_freq_pos, s.n_freq_dir);
+    if (items.size() >= 2) parse(items.front(), s.n_freq_pos0, s.n_freq_dir0);
+  }
+  auto ndc = cfg.find("useNDC");
+  s.use_ndc = (ndc != cfg.end() && strip(ndc->second) == "True") ? 1 : 0;   // config.cpp:265-266
+  if (s.use_ndc) {
+    // the reference's export does not record the image size (src/export.py:47-54); accept optional w / h / focal keys,
+    // otherwise ndc_rays uses the size of the frame being rendered (featureset.cpp:83-84)
+    float v = 0;
+    if (floats_of(info, "w", &v, 1)) s.ndc_w = int32_t(v);
+    if (floats_of(info, "h", &v, 1)) s.ndc_h = int32_t(v);
   }
   auto th = cfg.find("adaptiveSamplingThreshold");
   out.threshold = th == cfg.end() ? 0.0f : float(std::atof(strip(th->second).c_str()));
@@ -210,8 +220,14 @@ bool load_export_dir(const std::string& dir_in, ExportDir& out, std::string& err
     const auto items = list_items(it->second);
     return items.empty() || items.back() == want;
   };
-  if (!check("rayMarchSampler", "FromClassifiedDepthAdaptive") || !check("rayMarchNormalization", "InverseSqrtDistCentered") ||
-      !check("depthTransform", "log") || !check("accumulationMult", "alpha")) {
+  if (s.use_ndc) {
+    if (!check("rayMarchSampler", "FromClassifiedDepthAdaptiveNoDepthRange") || !check("rayMarchNormalization", "None") ||
+        !check("accumulationMult", "alpha")) {
+      err = "config.ini: NDC exports must use FromClassifiedDepthAdaptiveNoDepthRange / rayMarchNormalization None / alpha";
+      return false;
+    }
+  } else if (!check("rayMarchSampler", "FromClassifiedDepthAdaptive") || !check("rayMarchNormalization", "InverseSqrtDistCentered") ||
+             !check("depthTransform", "log") || !check("accumulationMult", "alpha")) {
     err = "config.ini: only FromClassifiedDepthAdaptive / InverseSqrtDistCentered / log / alpha exports are supported";
     return false;
   }

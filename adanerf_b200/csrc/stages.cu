@@ -82,7 +82,7 @@ cudaError_t launch_gen_dirs(const CameraRays& cam, long long n_rays, float* d_di
 
 // ------------------------------------------------------------------------------------ stage 0b
 // SpherePosDir.batch (src/features.py:845-899): one thread per ray.
-template <bool FROM_CAMERA>
+template <bool FROM_CAMERA, int NFD = kNFreqDir, int NFP = kNFreqPos>
 __global__ void __launch_bounds__(128)
 stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseDev pd, const float* __restrict__ dirs,
               const __grid_constant__ CameraRays cam, long long n_rays, float* __restrict__ x0, float* __restrict__ ray_o,
@@ -120,8 +120,9 @@ stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseD
     float dn[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) dn[a] = __fdiv_rn(nds[a], nn);
-    posenc3<kNFreqDir>(dn, f);                     // 27: direction block FIRST (:868)
-    posenc3<kNFreqPos>(p, f + 3 + 6 * kNFreqDir);  // 63
+    constexpr int F0 = 6 + 6 * (NFD + NFP);       // 90 ("10-4") or 30 ("2-2")
+    posenc3<NFD>(dn, f);                           // 27 / 15: direction block FIRST (:868)
+    posenc3<NFP>(p, f + 3 + 6 * NFD);              // 63 / 15
     if (ray_o) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -131,7 +132,7 @@ stage0_kernel(const __grid_constant__ SceneDev sc, const __grid_constant__ PoseD
     }
     if (x0) {
 #pragma unroll
-      for (int j = 0; j < kFeat; ++j) x0[i * kFeat + j] = f[j];
+      for (int j = 0; j < F0; ++j) x0[i * F0 + j] = f[j];
     }
   }
   if (tiles0) {
@@ -188,8 +189,12 @@ cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_
     cudaFuncSetAttribute(stage0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kBlkBytes);
     attr = true;
   }
-  if (cam) {
-    c = *cam;
+  if (cam) c = *cam;
+  if (sc.n_freq_pos0 == 2 && sc.n_freq_dir0 == 2) {   // "2-2": fp32 rows only (the generic pack kernel builds the tiles)
+    if (d_tiles0) return cudaErrorInvalidValue;
+    if (cam) stage0_kernel<true, 2, 2><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, nullptr);
+    else stage0_kernel<false, 2, 2><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, nullptr);
+  } else if (cam) {
     stage0_kernel<true><<<grid, 128, smem, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
   } else {
     stage0_kernel<false><<<grid, 128, smem, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
@@ -680,13 +685,36 @@ stage3_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ ray
         o[a] = __ldg(ray_o + 3 * r + a);
         d[a] = __ldg(ray_d + 3 * r + a);
       }
+      if (sc.ndc) {
+        // ndc_rays(H, W, focal, near = 1) (src/nerf_raymarch_common.py:71-88) in the reference's operation order, then
+        // pos = o' + d' z with the un-normalised NDC direction, no position normalisation, view encoding of d' / |d'|
+        const float t = __fdiv_rn(-__fadd_rn(1.0f, o[2]), d[2]);
+        float on[3];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) pos[a] = __fsub_rn(__fadd_rn(o[a], __fmul_rn(d[a], zw)), sc.c[a]);   // :458, loc = pos - c
-      // normalization_inverse_sqrt_dist_centered (src/nerf_raymarch_common.py:226-230)
-      const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(pos[0], pos[0]), __fmul_rn(pos[1], pos[1])), __fmul_rn(pos[2], pos[2])));
-      const float den = __fmul_rn(sc.sqrt_max_depth, __fsqrt_rn(nrm));
+        for (int a = 0; a < 3; ++a) on[a] = __fadd_rn(o[a], __fmul_rn(t, d[a]));
+        const float q0 = __fdiv_rn(on[0], on[2]), q1 = __fdiv_rn(on[1], on[2]);
+        const float o0 = __fdiv_rn(__fmul_rn(sc.ndc_cw, on[0]), on[2]);
+        const float o1 = __fdiv_rn(__fmul_rn(sc.ndc_ch, on[1]), on[2]);
+        const float o2 = __fadd_rn(1.0f, __fdiv_rn(2.0f, on[2]));
+        const float d0 = __fmul_rn(sc.ndc_cw, __fsub_rn(__fdiv_rn(d[0], d[2]), q0));
+        const float d1 = __fmul_rn(sc.ndc_ch, __fsub_rn(__fdiv_rn(d[1], d[2]), q1));
+        const float d2 = __fdiv_rn(-2.0f, on[2]);
+        pos[0] = __fadd_rn(o0, __fmul_rn(d0, zw));                                                    // :458
+        pos[1] = __fadd_rn(o1, __fmul_rn(d1, zw));
+        pos[2] = __fadd_rn(o2, __fmul_rn(d2, zw));
+        const float dn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+        d[0] = __fdiv_rn(d0, dn);                                                                     // :431
+        d[1] = __fdiv_rn(d1, dn);
+        d[2] = __fdiv_rn(d2, dn);
+      } else {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) pos[a] = __fdiv_rn(pos[a], den);
+        for (int a = 0; a < 3; ++a) pos[a] = __fsub_rn(__fadd_rn(o[a], __fmul_rn(d[a], zw)), sc.c[a]);   // :458, loc = pos - c
+        // normalization_inverse_sqrt_dist_centered (src/nerf_raymarch_common.py:226-230)
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(pos[0], pos[0]), __fmul_rn(pos[1], pos[1])), __fmul_rn(pos[2], pos[2])));
+        const float den = __fmul_rn(sc.sqrt_max_depth, __fsqrt_rn(nrm));
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pos[a] = __fdiv_rn(pos[a], den);
+      }
       posenc3<kNFreqPos>(pos, f);                      // 63: position block FIRST (:473-479)
       posenc3<kNFreqDir>(d, f + 64);                   // 27 (un-renormalised nds), staged at column 64
       if (x1) {
@@ -764,7 +792,9 @@ __device__ __forceinline__ void s5_write_ray_aux(const Stage5Aux& aux, long long
   if (aux.depth_map) aux.depth_map[r] = dm;
   if (aux.acc_map) aux.acc_map[r] = acc;
   if (aux.disp_map) aux.disp_map[r] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(dm, acc)));
-  if (aux.depth_est) {
+  if (aux.depth_est && aux.linear_depth) {
+    aux.depth_est[r] = dm;
+  } else if (aux.depth_est) {
     float d = __fsub_rn(dm, aux.dr_min);
     if (d <= 0.0f) d = 0.001f;
     aux.depth_est[r] = __fdiv_rn(logf(__fadd_rn(d, 1.0f)), aux.log_range);

@@ -12,6 +12,9 @@ struct SceneDev {
   float r2;            // float(view_cell_radius**2) (features.py:761,786)
   float sqrt_max_depth;  // float(math.sqrt(max_depth)) (nerf_raymarch_common.py:229)
   int n_freq_pos, n_freq_dir;
+  int n_freq_pos0, n_freq_dir0;   // sampling-net encoding (10/4 or 2/2)
+  int ndc;                        // NDC variant: ndc_rays + no position normalisation (features.py:429-431)
+  float ndc_cw, ndc_ch;           // float(-1 / (W / (2 focal))), float(-1 / (H / (2 focal)))
 };
 
 struct CameraRays {  // src/util/raygeneration.py:10-26 in double precision
@@ -55,6 +58,7 @@ struct Stage5Aux {
   float* acc_map = nullptr;     // [N] sum w
   float* disp_map = nullptr;    // [N] 1 / max(1e-10, depth_map / acc_map)
   float* depth_est = nullptr;   // [N] LogTransform.from_world(depth_map, depth_range) (NeRFOutputDepth)
+  int linear_depth = 0;         // NDC: depth_est = depth_map (features.py:573-574)
   float dr_min = 0.0f;          // depth_range[0]
   float log_range = 1.0f;       // float(log(depth_range[1] - depth_range[0] + 1))
   bool any() const { return weights || alpha || z_vals || depth_map || acc_map || disp_map || depth_est; }

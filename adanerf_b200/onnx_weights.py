@@ -138,14 +138,24 @@ def write_export_dir(path, scene, sd0, sd1, thr, K):
     as_np = lambda sd: {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in sd.items()}
     write_onnx_initializers(os.path.join(path, "model0.onnx"), as_np(sd0))
     write_onnx_initializers(os.path.join(path, "model1.onnx"), as_np(sd1))
+    ndc = bool(scene.get("use_ndc"))
     with open(os.path.join(path, "dataset_info.txt"), "w") as f:
         f.write(f"view_cell_center = {list(scene['view_cell_center'])}\n")
         f.write(f"view_cell_size = {list(scene['view_cell_size'])}\n")
         f.write(f"depth_range = {list(scene['depth_range'])}\n")
         f.write(f"fov = {scene['fov']}\nfocal = 0.0\ncamera_scale = 1.0\nmax_depth = {scene['max_depth']}\n")
+        if ndc and scene.get("w") and scene.get("h"):   # not written by src/export.py; read by our loader when present
+            f.write(f"w = {int(scene['w'])}\nh = {int(scene['h'])}\n")
     with open(os.path.join(path, "config.ini"), "w") as f:
-        f.write("posEnc = [nerf, nerf]\nposEncArgs = [10-4, 10-4]\ninFeatures = [SpherePosDir, RayMarchFromPoses]\n"
-                "outFeatures = [RawSigmoid, RGBARayMarch]\nrayMarchSampler = [none, FromClassifiedDepthAdaptive]\n"
-                "rayMarchNormalization = [InverseSqrtDistCentered, InverseSqrtDistCentered]\n"
-                f"numRaymarchSamples = [{K}, {K}]\ndepthTransform = log\nzNear = [0.001, 0.001]\nzFar = [1.0, 1.0]\n"
-                f"adaptiveSamplingThreshold = {thr}\nmultiDepthFeatures = [128, 128]\naccumulationMult = alpha\n")
+        if ndc:   # configs/fine_training_ndc.ini
+            f.write("posEnc = [nerf, nerf]\nposEncArgs = [2-2, 10-4]\ninFeatures = [SpherePosDir, RayMarchFromPoses]\n"
+                    "outFeatures = [RawSigmoid, RGBARayMarch]\nrayMarchSampler = [none, FromClassifiedDepthAdaptiveNoDepthRange]\n"
+                    "rayMarchNormalization = [InverseSqrtDistCentered, None]\nuseNDC = True\n"
+                    f"numRaymarchSamples = [{K}, {K}]\ndepthTransform = linear\nzNear = [0.001, 0.001]\nzFar = [1.0, 1.0]\n"
+                    f"adaptiveSamplingThreshold = {thr}\nmultiDepthFeatures = [128, 128]\naccumulationMult = alpha\n")
+        else:
+            f.write("posEnc = [nerf, nerf]\nposEncArgs = [10-4, 10-4]\ninFeatures = [SpherePosDir, RayMarchFromPoses]\n"
+                    "outFeatures = [RawSigmoid, RGBARayMarch]\nrayMarchSampler = [none, FromClassifiedDepthAdaptive]\n"
+                    "rayMarchNormalization = [InverseSqrtDistCentered, InverseSqrtDistCentered]\n"
+                    f"numRaymarchSamples = [{K}, {K}]\ndepthTransform = log\nzNear = [0.001, 0.001]\nzFar = [1.0, 1.0]\n"
+                    f"adaptiveSamplingThreshold = {thr}\nmultiDepthFeatures = [128, 128]\naccumulationMult = alpha\n")

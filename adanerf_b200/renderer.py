@@ -11,13 +11,19 @@ from ._lib import AdnError, AuxOutputs, Scene, Stats, TensorDesc
 
 
 def make_scene(view_cell_center, view_cell_size, depth_range, max_depth, fov, z_near=0.001, z_far=1.0,
-               n_freq_pos=10, n_freq_dir=4, **_):
+               n_freq_pos=10, n_freq_dir=4, use_ndc=False, w=0, h=0, focal=0.0, n_freq_pos0=None, n_freq_dir0=None, **_):
+    """use_ndc: the NDC / LLFF variant (configs/fine_training_ndc.ini); w, h, focal = the dataset's image size and focal
+    length that ndc_rays uses (src/features.py:350-351,430); the sampling net then takes the "2-2" encoding (30 features)
+    unless n_freq_pos0 / n_freq_dir0 say otherwise."""
     s = Scene()
     s.view_cell_center[:] = [float(x) for x in view_cell_center]
     s.view_cell_size[:] = [float(x) for x in view_cell_size]
     s.depth_range[:] = [float(x) for x in depth_range]
     s.max_depth, s.fov, s.z_near, s.z_far = float(max_depth), float(fov), float(z_near), float(z_far)
     s.n_freq_pos, s.n_freq_dir = int(n_freq_pos), int(n_freq_dir)
+    s.use_ndc, s.ndc_w, s.ndc_h, s.ndc_focal = int(bool(use_ndc)), int(w or 0), int(h or 0), float(focal or 0.0)
+    s.n_freq_pos0 = int(n_freq_pos0) if n_freq_pos0 is not None else (2 if use_ndc else 0)
+    s.n_freq_dir0 = int(n_freq_dir0) if n_freq_dir0 is not None else (2 if use_ndc else 0)
     return s
 
 
@@ -40,11 +46,14 @@ class Renderer:
         self.lib = _lib.load_library()
         self.device = int(device)
         self.handle = C.c_void_p()
+        self.n_feat0 = 90        # sampling-net input features (30 with the "2-2" encoding of the NDC configs)
         if _handle is not None:
             self.handle = _handle
         else:
             sc = scene if isinstance(scene, Scene) else make_scene(**scene)
             self._check(self.lib.adn_create(C.byref(self.handle), C.byref(sc), self.device), create=True)
+            if sc.n_freq_pos0 or sc.n_freq_dir0:
+                self.n_feat0 = 6 + 6 * (sc.n_freq_pos0 + sc.n_freq_dir0)
         if sampling_net is not None:
             self.set_weights(0, sampling_net)
         if shading_net is not None:
@@ -58,7 +67,11 @@ class Renderer:
         st = lib.adn_create_from_export_dir(C.byref(h), str(path).encode(), int(device), C.byref(thr), C.byref(k))
         if st != 0:
             raise AdnError(st, f"loading export dir {path}")
-        return cls(None, device=device, _handle=h), float(thr.value), int(k.value)
+        r = cls(None, device=device, _handle=h)
+        sc, nt = Scene(), (C.c_int * 2)()
+        if lib.adn_probe_export_dir(str(path).encode(), C.byref(sc), None, None, nt) == 0 and (sc.n_freq_pos0 or sc.n_freq_dir0):
+            r.n_feat0 = 6 + 6 * (sc.n_freq_pos0 + sc.n_freq_dir0)
+        return r, float(thr.value), int(k.value)
 
     def _check(self, st, create=False):
         if st != 0:
@@ -214,7 +227,7 @@ class Renderer:
         p, r = self._pose_rot(pose, rot)
         d = self._f32(dirs).reshape(-1, 3)
         n = d.shape[0]
-        x0 = torch.empty((n, 90), dtype=torch.float32, device=self._dev())
+        x0 = torch.empty((n, self.n_feat0), dtype=torch.float32, device=self._dev())
         ro = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
         rd = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
         self._check(self.lib.adn_stage0_features(self.handle, _fptr(p), _fptr(r), d.data_ptr(), n, x0.data_ptr(),

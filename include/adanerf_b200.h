@@ -46,8 +46,19 @@ typedef struct adn_scene {
   float max_depth;
   float fov;            /* radians; focal = 0.5*W/tan(fov/2)  (src/datasets.py:181-182) */
   float z_near, z_far;  /* 0.001, 1.0 */
-  int32_t n_freq_pos;   /* 10 */
+  int32_t n_freq_pos;   /* 10: shading-net encoding, posEncArgs[1] = "10-4" */
   int32_t n_freq_dir;   /* 4 */
+  /* Sampling-net encoding, posEncArgs[0]: 0/0 = same as above ("10-4", 90 features) or 2/2 ("2-2", 30 features,
+   * configs/fine_training_ndc.ini:8). */
+  int32_t n_freq_pos0, n_freq_dir0;
+  /* NDC / LLFF variant (configs/fine_training_ndc.ini: useNDC, FromClassifiedDepthAdaptiveNoDepthRange,
+   * rayMarchNormalization[1] = None): rays go through ndc_rays(H, W, focal, near = 1)
+   * (src/nerf_raymarch_common.py:71-88, src/features.py:429-431), sample depths are the cell centres in [0,1]
+   * (no depth-range warp), positions are not normalised, NeRFOutputDepth is the depth map itself.
+   * ndc_w / ndc_h: the dataset's image size (features.py:350-351); ndc_focal <= 0 -> 0.5 * ndc_w / tan(fov / 2). */
+  int32_t use_ndc;
+  int32_t ndc_w, ndc_h;
+  float ndc_focal;
 } adn_scene;
 
 /* One named parameter tensor, fp32, row-major [rows, cols] ([out, in] for weights, [out, 1] or

@@ -110,3 +110,36 @@ def test_weights_checkpoints_to_export_dir(lib, tmp_path):
     torch.save(bad, tmp_path / "bad.weights")
     with pytest.raises(ValueError, match="views_linears"):
         convert.weights_to_export_dir(tmp_path / "Net0_opt.weights", tmp_path / "bad.weights", tmp_path / "x", scene, 0.2, 8)
+
+
+def test_cxx_loader_reads_ndc_export(lib, tmp_path):
+    """configs/fine_training_ndc.ini exports: useNDC, [2-2, 10-4], NoDepthRange sampler, normalisation None."""
+    sd0, sd1 = orc.make_weights("ndc", seed=0)
+    d = tmp_path / "ndc"
+    ow.write_export_dir(str(d), orc.SCENE_PAVILLON_NDC, sd0, sd1, 0.15, 16)
+    from adanerf_b200._lib import Scene
+    sc, thr, K, nt = Scene(), C.c_float(), C.c_int(), (C.c_int * 2)()
+    assert lib.adn_probe_export_dir(str(d).encode(), C.byref(sc), C.byref(thr), C.byref(K), nt) == 0
+    assert (sc.use_ndc, sc.n_freq_pos0, sc.n_freq_dir0, sc.n_freq_pos, sc.n_freq_dir) == (1, 2, 2, 10, 4)
+    assert (sc.ndc_w, sc.ndc_h, K.value) == (800, 800, 16)
+    # an NDC flag with the depth-range sampler is inconsistent -> rejected
+    cfg = (d / "config.ini").read_text().replace("FromClassifiedDepthAdaptiveNoDepthRange", "FromClassifiedDepthAdaptive")
+    (d / "config.ini").write_text(cfg)
+    assert lib.adn_probe_export_dir(str(d).encode(), C.byref(sc), C.byref(thr), C.byref(K), nt) == 5
+
+
+@pytest.mark.gpu
+def test_render_from_ndc_export_dir_matches_state_dict(tmp_path):
+    from adanerf_b200 import Renderer
+    scene = orc.SCENE_PAVILLON_NDC
+    sd0, sd1 = orc.make_weights("ndc", seed=0)
+    d = tmp_path / "export_ndc"
+    ow.write_export_dir(str(d), scene, sd0, sd1, 0.15, 16)
+    r1, thr, K = Renderer.from_export_dir(str(d))
+    r2 = Renderer(scene, sampling_net=sd0, shading_net=sd1)
+    pose, rot = torch.tensor(scene["view_cell_center"]), torch.eye(3)
+    a = r1.render_camera(pose, rot, 200, 160, thr, K)["rgb"]
+    b = r2.render_camera(pose, rot, 200, 160, 0.15, 16)["rgb"]
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    r1.close()
+    r2.close()

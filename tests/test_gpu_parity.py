@@ -482,3 +482,65 @@ def test_image_metrics_on_device(bare):
     assert again == m                                              # deterministic reduction
     with pytest.raises(Exception):
         bare.image_metrics(a.cuda(), b[:10].cuda())
+
+
+# ------------------------------------------------------------------------------------ NDC / LLFF variant
+def test_ndc_variant_stages_and_render():
+    """configs/fine_training_ndc.ini: 30-feature sampling net ("2-2"), FromClassifiedDepthAdaptiveNoDepthRange (z = cell
+    centre), ndc_rays + un-normalised positions in stage 3, NeRFOutputDepth = depth map -- against the reference's own
+    tensors (golden case ndc_k16_t0.15)."""
+    g = load_golden("ndc_k16_t0.15")
+    m = g["meta"]
+    K, thr, scene = m["K"], m["thr"], m["scene_params"]
+    assert scene["use_ndc"] and g["x0"].shape[1] == 30
+    sd0, sd1 = case_weights("ndc_k16_t0.15")
+    r = _renderer(scene, sd0, sd1)
+    dirs = torch.from_numpy(g["dirs"]).cuda()
+    # stage 0: "2-2" encoding, direction block first
+    x0, ro, rd = r.stage0(g["pose"], g["rot"], dirs)
+    assert x0.shape == (g["dirs"].shape[0], 30)
+    np.testing.assert_array_equal(rd.cpu().numpy(), g["ray_d"])
+    np.testing.assert_allclose(ro.cpu().numpy(), g["ray_o"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(x0.cpu().numpy(), g["x0"], rtol=0, atol=2e-5)
+    # stage 1 on the reference's features (bf16x3 split precision, K = 30 padded)
+    raw0 = r.mlp0(torch.from_numpy(g["x0"]).cuda())
+    np.testing.assert_allclose(raw0.cpu().numpy(), g["raw0"], rtol=0, atol=2e-4 * max(1.0, np.abs(g["raw0"]).max()))
+    # stage 2 on the reference's raw0: bit-exact selection, z = (cell + 0.5) / 128 exactly
+    s2 = r.stage2(torch.from_numpy(g["raw0"]).cuda(), thr, K)
+    mask, ray, z = _packed_from_golden(g, K)
+    np.testing.assert_array_equal(s2["count"].cpu().numpy(), mask.sum(1))
+    np.testing.assert_array_equal(s2["ray"].cpu().numpy(), ray)
+    np.testing.assert_array_equal(s2["z"].cpu().numpy(), z)
+    np.testing.assert_array_equal(s2["z"].cpu().numpy(), (s2["cell"].cpu().numpy() + 0.5) / 128.0)
+    # stage 3: ndc_rays, no normalisation
+    x1 = r.stage3(torch.from_numpy(g["ray_o"]), torch.from_numpy(g["ray_d"]), torch.from_numpy(ray.astype(np.int32)),
+                  torch.from_numpy(z)).cpu().numpy()
+    ref = g["x1_nan"].reshape(-1, 90)[mask.flatten()]
+    err = np.abs(x1 - ref)
+    assert np.abs(x1[:, :3] - ref[:, :3]).max() < 2e-5 * max(1.0, np.abs(ref[:, :3]).max())     # NDC positions
+    assert err[:, 63:].max() < 2e-5                                                             # view encoding
+    assert err[:, :63].max() < 5e-3, err[:, :63].max()    # 2^9 band on |x| up to ~7 (un-normalised NDC coordinates)
+    # end to end + auxiliaries
+    out = r.render_rays(g["pose"], g["rot"], dirs, thr, K, want_aux=True)
+    ns = out["n_samples"].cpu().numpy()
+    same = ns == np.round(g["asp"] * K).astype(np.int32)
+    assert same.mean() >= 0.98
+    rgb = out["rgb"].cpu().numpy()
+    p = orc.psnr(rgb[same], g["rgb"][same])
+    print(f"ndc: identical counts {same.mean():.4f}, PSNR {p:.2f} dB")
+    assert p > 40.0
+    np.testing.assert_allclose(out["z_vals"].cpu().numpy()[same], g["z_nan"][same], rtol=0, atol=0, equal_nan=True)
+    np.testing.assert_array_equal(out["depth_est"].cpu().numpy(), out["depth_map"].cpu().numpy())   # features.py:573-574
+    assert np.abs(out["depth_est"].cpu().numpy()[same] - g["depth_est"][same, 0]).max() < 5e-2
+    # camera entry: the frame size feeds ndc_rays (800 x 800 here = the scene's w, h): same as explicit rays
+    cam = r.render_camera(g["pose"], g["rot"], 800, 800, thr, K, row0=0, rows=4)["rgb"]
+    dirs_all = torch.from_numpy(orc.generate_ray_directions(800, 800, scene["fov"]).reshape(-1, 3)).float()[:4 * 800].cuda()
+    exp = r.render_rays(g["pose"], g["rot"], dirs_all, thr, K)["rgb"]
+    assert torch.equal(cam, exp)
+    r.close()
+    # a 90-feature sampling net is rejected for this scene, with a message
+    bad0, _ = orc.make_weights("rand", seed=0)
+    r2 = _renderer(scene, bad0, sd1)
+    with pytest.raises(Exception, match="30"):
+        r2.render_rays(g["pose"], g["rot"], dirs, thr, K)
+    r2.close()
