@@ -44,6 +44,8 @@ class B200Inference:
         scene = dict(view_cell_center=list(info.view.view_cell_center), view_cell_size=list(info.view.view_cell_size),
                      depth_range=list(f1.depth_range), max_depth=float(f1.max_depth), fov=float(info.view.fov),
                      z_near=f1.z_near, z_far=f1.z_far)
+        if getattr(f1, "useNDC", False):    # configs/*_ndc.ini: ndc_rays(self.h, self.w, self.view.focal, 1., ...) (features.py:430)
+            scene.update(use_ndc=True, w=int(f1.w), h=int(f1.h), focal=float(info.view.focal))
         return cls(scene, train_config.models[0], train_config.models[1], f1.z_sampler.threshold, f1.n_ray_samples, device=device)
 
     def inference(self, batch_idx, gradient=False, **kwargs):
