@@ -205,12 +205,20 @@ def run_ours(args, cfg, name):
     import __graft_entry__ as ge
     ge.build()
     from adanerf_b200 import Renderer
-    from oracle import adanerf_oracle as orc   # weights / ray generation helpers + the cpu_baseline leg only
-    scene = orc.SCENE_BARBERSHOP
-    sd0, sd1 = orc.make_weights(cfg["weights"], seed=0)
-    r = Renderer(scene, device=local, sampling_net=sd0, shading_net=sd1)
+    from adanerf_b200 import synthetic   # product-side synthetic scene / weights; nothing under oracle/ on this arm
+    scene = synthetic.SCENE_BARBERSHOP
     pose = torch.tensor(scene["view_cell_center"], dtype=torch.float32)
     rot = torch.eye(3)
+    r = Renderer(scene, device=local)
+
+    def probe_logits(sd0):   # W-shaped recipe: raw sampling-net outputs on every 157th ray of the 800x800 grid
+        r.set_weights(0, sd0)
+        x0, _, _ = r.stage0(pose, rot, r.generate_ray_directions(W, H)[::157].contiguous())
+        return r.mlp0(x0)
+
+    sd0, sd1 = synthetic.make_weights(cfg["weights"], seed=0, logits_fn=probe_logits)
+    r.set_weights(0, sd0)
+    r.set_weights(1, sd1)
     Hn = H * world                 # weak scaling: an 800 x 800N frame, one 800-row band per rank
     row0 = H * rank
     thr, K = cfg["thr"], cfg["K"]
@@ -253,8 +261,7 @@ def run_ours(args, cfg, name):
     value = world * 1000.0 / ms_per_step          # 800x800-frame equivalents per second, all ranks
 
     # ---- end to end through the host-buffer entry point (H2D dirs + D2H rgb inside the timed region)
-    dirs_host = np.ascontiguousarray(orc.generate_ray_directions(W, Hn, scene["fov"], 0.5 * W / np.tan(0.5 * scene["fov"]))
-                                     .reshape(-1, 3)[row0 * W:(row0 + H) * W].astype(np.float32))
+    dirs_host = np.ascontiguousarray(r.generate_ray_directions(W, Hn, row0=row0, rows=H).cpu().numpy())   # this rank's band
     rgb_host = np.empty((n_rays, 3), dtype=np.float32)   # caller-owned result buffer, reused every frame
     for _ in range(3):
         r.render_rays_host(pose, rot, dirs_host, thr, K, want_nsamples=False, out=rgb_host)

@@ -36,15 +36,13 @@ SCENE_PAVILLON = dict(
     view_cell_center=[0.783, -3.19, 1.39], view_cell_size=[0.7, 0.7, 0.2],
     depth_range=[0.1542200982570648, 8.358194804191589], fov=1.1386263370513916,
     max_depth=8.79825210571289)
+# the NDC / LLFF variant (configs/fine_training_ndc.ini) on the same geometry: dataset w, h feed ndc_rays (features.py:430)
+SCENE_PAVILLON_NDC = dict(SCENE_PAVILLON, use_ndc=True, w=800, h=800)
 
 
 # ----------------------------------------------------------------------------------------------
 # stage 0a: pixel ray directions -- src/util/raygeneration.py:10-26 (float64 numpy, like the ref)
 # ----------------------------------------------------------------------------------------------
-# the NDC / LLFF variant (configs/fine_training_ndc.ini) on the same geometry: dataset w, h feed ndc_rays (features.py:430)
-SCENE_PAVILLON_NDC = dict(SCENE_PAVILLON, use_ndc=True, w=800, h=800)
-
-
 def generate_ray_directions(w, h, fov, focal=None):
     if focal is None:
         focal = 0.5 * w / math.tan(0.5 * fov)  # src/datasets.py:181-182

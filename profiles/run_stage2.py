@@ -8,10 +8,9 @@ import __graft_entry__ as ge
 def main():
     ge.build()
     from adanerf_b200 import Renderer
-    from oracle import adanerf_oracle as orc   # weight / scene helpers only
-    which = sys.argv[1] if len(sys.argv) > 1 else "rand"
-    scene = orc.SCENE_BARBERSHOP
-    sd0, sd1 = orc.make_weights(which, seed=0)
+    from adanerf_b200 import synthetic
+    scene = synthetic.SCENE_BARBERSHOP
+    sd0, sd1 = synthetic.make_weights("rand", seed=0)
     r = Renderer(scene, device=0, sampling_net=sd0, shading_net=sd1)
     pose = torch.tensor(scene["view_cell_center"], dtype=torch.float32)
     dirs = r.generate_ray_directions(800, 800)

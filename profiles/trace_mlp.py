@@ -7,11 +7,11 @@ import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adanerf_b200 import Renderer
-from oracle import adanerf_oracle as orc
+from adanerf_b200 import synthetic
 
 net = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-scene = orc.SCENE_BARBERSHOP
-sd0, sd1 = orc.make_weights("rand", seed=0)
+scene = synthetic.SCENE_BARBERSHOP
+sd0, sd1 = synthetic.make_weights("rand", seed=0)
 r = Renderer(scene, device=0, sampling_net=sd0, shading_net=sd1)
 pose = torch.tensor(scene["view_cell_center"]); rot = torch.eye(3)
 for _ in range(2):
