@@ -812,23 +812,37 @@ stage5_thread_kernel(const float4* __restrict__ raw1, const float* __restrict__ 
   const int n = count[r];
   const bool want_z = aux.depth_map || aux.disp_map || aux.depth_est || aux.z_vals;
   float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, dm = 0.0f, acc = 0.0f;
-  for (int j = 0; j < n; ++j) {
-    const float4 q = __ldg(raw1 + off + j);
-    const float sr = sigmoidf_acc(q.x), sg = sigmoidf_acc(q.y), sb = sigmoidf_acc(q.z), sa = sigmoidf_acc(q.w);
-    const float alpha = __fmul_rn(sa, __ldg(zp + off + j));                       // :123-125
-    const float w = __fmul_rn(alpha, T);                                          // :128-129
-    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
-    cr = __fadd_rn(cr, __fmul_rn(w, sr));                                         // :135
-    cg = __fadd_rn(cg, __fmul_rn(w, sg));
-    cb = __fadd_rn(cb, __fmul_rn(w, sb));
-    acc = __fadd_rn(acc, w);                                                      // :139
-    if (want_z) {
-      const float zz = __ldg(z + off + j);
-      dm = __fadd_rn(dm, __fmul_rn(w, zz));                                       // :137
-      if (aux.z_vals) aux.z_vals[r * K + j] = zz;
+  for (int j0 = 0; j0 < n; j0 += 4) {
+    // four samples' loads are issued before the (sequential) transmittance chain consumes them
+    float4 q4[4];
+    float zp4[4], z4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool live = j0 + u < n;
+      q4[u] = live ? __ldg(raw1 + off + j0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zp4[u] = live ? __ldg(zp + off + j0 + u) : 0.0f;
+      z4[u] = (live && want_z) ? __ldg(z + off + j0 + u) : 0.0f;
     }
-    if (aux.weights) aux.weights[r * K + j] = w;
-    if (aux.alpha) aux.alpha[r * K + j] = alpha;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      if (j >= n) break;
+      const float4 q = q4[u];
+      const float sr = sigmoidf_acc(q.x), sg = sigmoidf_acc(q.y), sb = sigmoidf_acc(q.z), sa = sigmoidf_acc(q.w);
+      const float alpha = __fmul_rn(sa, zp4[u]);                                    // :123-125
+      const float w = __fmul_rn(alpha, T);                                          // :128-129
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+      cr = __fadd_rn(cr, __fmul_rn(w, sr));                                         // :135
+      cg = __fadd_rn(cg, __fmul_rn(w, sg));
+      cb = __fadd_rn(cb, __fmul_rn(w, sb));
+      acc = __fadd_rn(acc, w);                                                      // :139
+      if (want_z) {
+        dm = __fadd_rn(dm, __fmul_rn(w, z4[u]));                                    // :137
+        if (aux.z_vals) aux.z_vals[r * K + j] = z4[u];
+      }
+      if (aux.weights) aux.weights[r * K + j] = w;
+      if (aux.alpha) aux.alpha[r * K + j] = alpha;
+    }
   }
   for (int j = n; j < K; ++j) {
     if (aux.weights) aux.weights[r * K + j] = 0.0f;

@@ -544,3 +544,20 @@ def test_ndc_variant_stages_and_render():
     with pytest.raises(Exception, match="30"):
         r2.render_rays(g["pose"], g["rot"], dirs, thr, K)
     r2.close()
+
+
+def test_render_k32_uses_the_general_kernels():
+    """16 < K < 128: warp-per-ray top-K (stage2_kernel) and the warp-per-ray composite, end to end against the oracle."""
+    scene = orc.SCENE_BARBERSHOP
+    sd0, sd1 = orc.make_weights("shaped", seed=0)
+    r = _renderer(scene, sd0, sd1)
+    pose, rot = torch.tensor(scene["view_cell_center"]), orc.rotation_yaw(90.0)
+    dirs = torch.from_numpy(orc.generate_ray_directions(800, 800, scene["fov"]).reshape(-1, 3)).float()[::311][:2000]
+    for K, thr in ((32, 0.05), (64, 0.0125), (24, 0.2)):
+        ref = orc.render_rays(pose, rot, dirs, sd0, sd1, scene, thr, K)
+        out = r.render_rays(pose, rot, dirs.cuda(), thr, K)
+        same = (out["n_samples"].cpu().long() == ref["n_samples"]).float().mean().item()
+        p = orc.psnr(out["rgb"].cpu().numpy(), ref["rgb"].numpy())
+        print(f"K={K} thr={thr}: mean spr {ref['n_samples'].float().mean():.2f}, identical counts {same:.4f}, PSNR {p:.2f} dB")
+        assert same >= 0.995 and p > 45.0
+    r.close()
