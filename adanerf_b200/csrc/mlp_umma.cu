@@ -174,7 +174,10 @@ __device__ __forceinline__ int layer_stages(const MlpLayer& L) {
 template <int NSPLIT, int CG>
 struct RingCfg {
   static constexpr int kStageBytes = 2 * kBlkBytes / CG;
-  static constexpr int kStages = ((NSPLIT == 2) ? 3 : 2) * CG;
+#ifndef ADN_BF16_PAIR_STAGES
+#define ADN_BF16_PAIR_STAGES 4   // ring stages of the shading kernel's CTA pair (sensitivity experiments: 3)
+#endif
+  static constexpr int kStages = (NSPLIT == 1 && CG == 2) ? ADN_BF16_PAIR_STAGES : ((NSPLIT == 2) ? 3 : 2) * CG;
 };
 
 template <int NSPLIT, int NG, int CG>
