@@ -104,7 +104,9 @@ adn_status adn_create_from_export_dir(adn_ctx** out, const char* dir, int device
 adn_status adn_probe_export_dir(const char* dir, adn_scene* scene_out, float* thr_out, int* k_out, int* n_tensors_out /*[2]*/);
 
 /* name: "chunk_rays" (rays per internal batch, 0 = auto), "profile" (0/1 per-stage event timing),
- * "mlp0_terms" (3 = bf16x3 split precision [default], 1 = plain bf16; parity experiments only). */
+ * "mlp0_terms" (3 = bf16x3 split precision [default], 1 = plain bf16; parity experiments only),
+ * "cta_group" (2 = CTA-pair MMAs [default], 1 = single-CTA MMAs; A/B runs),
+ * "trace" (debug: net id whose MLP kernel records an in-kernel timeline, -1 = off; profiles/trace_mlp.py). */
 adn_status adn_set_option(adn_ctx* ctx, const char* name, int64_t value);
 adn_status adn_get_stats(adn_ctx* ctx, adn_stats* out);   /* synchronises the context's stream */
 
