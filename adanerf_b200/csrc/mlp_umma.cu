@@ -2,7 +2,10 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "mlp_umma.cuh"
+#include "posenc.cuh"
 #include "ptx.cuh"
 
 namespace adn {
@@ -186,11 +189,13 @@ constexpr size_t mlp_smem_layout_bytes() {
          512 /*barriers*/ + 1024 /*alignment slack*/;
 }
 
-template <int NSPLIT, int NG, int CG>
-__global__ void __launch_bounds__(kMlpThreads, 1)
+template <int NSPLIT, int NG, int CG, bool ENC = false>
+__global__ void __launch_bounds__(ENC ? kMlpEncThreads : kMlpThreads, 1)
 mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict__ wblob,
                 const uint8_t* __restrict__ in_tiles, float* __restrict__ out,
-                const long long* __restrict__ rows_dev, long long rows_host, int* err_flag, long long* trace) {
+                const long long* __restrict__ rows_dev, long long rows_host, int* err_flag, long long* trace,
+                const __grid_constant__ EncodeParams enc) {
+  static_assert(!ENC || NSPLIT == 1, "fused input encoder: shading net (plain bf16) only");
   using Cfg = MlpCfg<NSPLIT>;
   using Ring = RingCfg<NSPLIT, CG>;
   constexpr int NB = Cfg::kNB;
@@ -200,7 +205,10 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   constexpr int EW = 16;        // epilogue warps: every one of them serves all NG tile slots in turn
   constexpr int QW = EW / 4;    // warps sharing one TMEM lane quarter (they split the columns)
   constexpr int CW = 128 / QW;  // accumulator columns per warp and N half
-  constexpr int kProducerWarp = 16, kHelperWarp = 17, kMmaWarp = 18;   // highest warp ids: favoured by the issue arbiter
+  // ENC: warp 16 encodes the tile inputs.  (As warp 0 -- lowest issue priority -- it starves behind its sub-partition's
+  // epilogue warps and the MMAs end up waiting for input images: measured 6.3 ms against 5.8 ms.)
+  constexpr int kEncWarp = 16;
+  constexpr int kProducerWarp = ENC ? 17 : 16, kHelperWarp = kProducerWarp + 1, kMmaWarp = kProducerWarp + 2;   // highest warp ids: favoured by the issue arbiter
   constexpr int kBarSlot = 3, kBarStage = 5;   // named barrier ids (1, 2 are used by the epilogue warps)
 
   extern __shared__ uint8_t smem_raw[];
@@ -216,7 +224,9 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
   uint64_t* peer_act = act_ready + NG;         // [NG]  leader only: the peer's act_ready, forwarded by its helper warp
   uint64_t* in_full = peer_act + NG;           // [NG]  this CTA's tile input has landed
   uint64_t* peer_in = in_full + NG;            // [NG]  leader only: the peer's tile input has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_in + NG);
+  uint64_t* enc_ready = peer_in + NG;          // [NG]  ENC: the encoder warp has written the next tile's input image
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_ready + NG);
+  volatile int* tiles_done = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [NG] ENC: tiles of the slot whose last layer has retired
 
   // warp index through a lane-0 broadcast: tells the compiler it is warp uniform, so the role branches
   // (and everything indexed by loop counters inside them) stay on the uniform datapath
@@ -242,6 +252,8 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
       mbar_init(&peer_act[g], 1);
       mbar_init(&in_full[g], 1);
       mbar_init(&peer_in[g], 1);
+      mbar_init(&enc_ready[g], 1);
+      tiles_done[g] = 0;
     }
     mbar_fence_init();
   }
@@ -253,6 +265,10 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
 
   auto act_ptr = [&](int g, int term, int blk) -> uint8_t* {
     return act + (size_t(g * NSPLIT + term) * NB + blk) * kBlkBytes;
+  };
+  // ENC: this CTA's input images in global memory (L2 resident), double buffered per slot: [P block | V block]
+  auto enc_scratch = [&](int g, long long iter) -> uint8_t* {
+    return enc.scratch + ((size_t(blockIdx.x) * NG + g) * 2 + size_t(iter & 1)) * (2 * kBlkBytes);
   };
   // first tile of the unit's tile group for (iter, slot); CTA `cta_rank` of a pair owns tile first + cta_rank
   auto first_tile = [&](long long iter, int g) -> long long { return ((iter * n_units + unit) * NG + g) * CG; };
@@ -475,6 +491,81 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
         }
       }
     }
+  } else if (ENC && warp == kEncWarp) {
+    // ============================================================================ input encoder (stage 3, fused)
+    // One warp, four tile rows per lane (rows lane + 32 q).  It runs up to two tiles ahead of the MMAs: for every tile
+    // it computes the position block P and the view block V (RayMarchFromPoses.batch, features.py:458-479, same device
+    // functions as stage3_kernel) and writes the swizzled bf16 image into this CTA's double-buffered scratch in global
+    // memory (19 MB for the whole grid: L2 resident), from where the usual bulk copies fetch it -- P at the tile
+    // start, V once the skip layer has retired.  The [M, 90] feature tensor never exists and the encoding is off the
+    // critical path.  Buffer reuse: the image of tile t - 2 is dead when that tile's last layer has retired.
+    auto store_row = [&](uint8_t* blk, int row, const float (&v)[3], bool live, auto L_tag) {
+      constexpr int L = decltype(L_tag)::value;
+      float f[64];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) f[k] = 0.0f;
+      if (live) posenc3<L>(v, f);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float* q = f + ch * 8;
+        const uint4 hi = make_uint4(bf16x2(q[0], q[1]), bf16x2(q[2], q[3]), bf16x2(q[4], q[5]), bf16x2(q[6], q[7]));
+        *reinterpret_cast<uint4*>(blk + sw128_offset(uint32_t(row), uint32_t(ch * 8))) = hi;
+      }
+    };
+    using L10 = std::integral_constant<int, 10>;
+    using L4 = std::integral_constant<int, 4>;
+    for (long long iter = 0;; ++iter) {
+      if (first_tile(iter, 0) >= n_tiles) break;
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g) {
+        if (first_tile(iter, g) >= n_tiles) continue;
+        const long long t = first_tile(iter, g) + cta_rank;
+        if (iter >= 2) {   // the image buffer still belongs to tile iter - 2 until that tile's last layer has retired
+          const long long t0 = clock64();
+          while (tiles_done[g] < int(iter) - 1) {
+            __nanosleep(200);
+            if (clock64() - t0 > ADN_WATCHDOG_CYCLES) {
+              if (err_flag) atomicExch(err_flag, 0x1000 + 10);
+              asm volatile("trap;");
+            }
+          }
+        }
+        uint8_t* img = enc_scratch(g, iter);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const int row = lane + 32 * q;
+          const long long i = t * kTileM + row;
+          const bool live = i < rows;
+          float pos[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+          if (live) {
+            long long ray;
+            float zw;
+            if (enc.ray_idx) {
+              ray = enc.ray_idx[i];
+              zw = enc.z[i];
+            } else {
+              ray = i / enc.K;
+              zw = enc.zlut_dense[i - ray * enc.K];
+            }
+            // pos = o + d z, then normalization_inverse_sqrt_dist_centered (same operation order as stage3_kernel)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              d[a] = __ldg(enc.ray_d + 3 * ray + a);
+              pos[a] = __fsub_rn(__fadd_rn(__ldg(enc.ray_o + 3 * ray + a), __fmul_rn(d[a], zw)), enc.c[a]);
+            }
+            const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(pos[0], pos[0]), __fmul_rn(pos[1], pos[1])), __fmul_rn(pos[2], pos[2])));
+            const float den = __fmul_rn(enc.sqrt_max_depth, __fsqrt_rn(nrm));
+#pragma unroll
+            for (int a = 0; a < 3; ++a) pos[a] = __fdiv_rn(pos[a], den);
+          }
+          store_row(img, row, pos, live, L10{});                 // P: 63 position features + 0
+          store_row(img + kBlkBytes, row, d, live, L4{});        // V: 27 direction features + zeros
+        }
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&enc_ready[g]);
+      }
+    }
   } else {
     // ============================================================================ epilogue
     // All 16 warps serve BOTH tile slots, alternating (layer l slot 0, layer l slot 1, layer l+1 slot 0, ...): the
@@ -491,8 +582,12 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
     auto tile_prologue = [&](long long iter, int g) {
       const long long t = first_tile(iter, g) + cta_rank;
       if (e == 0 && lane == 0) {
+        if (ENC) {   // the encoder warp has written this tile's [P | V] image (generic proxy) -> read by the TMA engine
+          mbar_wait(&enc_ready[g], uint32_t(iter) & 1u, err_flag, 12);
+          fence_proxy_async_all();
+        }
         if (t < n_tiles) {
-          const uint8_t* src = in_tiles + size_t(t) * prog.in_tile_stride;
+          const uint8_t* src = ENC ? enc_scratch(g, iter) : in_tiles + size_t(t) * prog.in_tile_stride;
           const uint32_t bytes = uint32_t(prog.in0_nblk) * kBlkBytes;
           mbar_arrive_expect_tx(&in_full[g], bytes * NSPLIT);
           bulk_g2s(act_ptr(g, 0, prog.in0_blk), src + prog.in0_off, bytes, &in_full[g]);
@@ -531,11 +626,14 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
           acc_phase ^= (1u << g);
           tc_fence_after();
           if (lane == 0 && (e == 0 || e == EW - 1)) tr(1 + 2 * g + (e != 0), g, l, 3);
+          // last layer retired -> both bulk copies of this tile's input image were consumed long ago: the encoder
+          // warp may overwrite that buffer (monotonic counter: a late reader can not mistake one tile for another)
+          if (ENC && l + 1 == prog.n_layers && e == 0 && lane == 0) tiles_done[g] = int(iter) + 1;
           if ((L.flags & LF_LOAD_IN1_AFTER) && e == 0 && lane == 0) {
             if (have_tile) {
+              const uint8_t* src = ENC ? enc_scratch(g, iter) : in_tiles + size_t(t) * prog.in_tile_stride;
               mbar_arrive_expect_tx(&in_full[g], kBlkBytes);
-              bulk_g2s(act_ptr(g, 0, prog.in1_blk), in_tiles + size_t(t) * prog.in_tile_stride + prog.in1_off, kBlkBytes,
-                       &in_full[g]);
+              bulk_g2s(act_ptr(g, 0, prog.in1_blk), src + prog.in1_off, kBlkBytes, &in_full[g]);
             } else {
               mbar_arrive(&in_full[g]);
             }
@@ -985,13 +1083,14 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, long long rows_hos
 }
 
 // -------------------------------------------------------------------------------------------------
-template <int NSPLIT, int NG, int CG>
+template <int NSPLIT, int NG, int CG, bool ENC = false>
 static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles,
                                 float* out, const long long* rows_dev, long long rows_host, int* err_flag, int num_sms,
-                                cudaStream_t stream, long long* trace) {
+                                cudaStream_t stream, long long* trace, const EncodeParams* encp = nullptr) {
   static bool attr_set = false;
   const size_t smem = mlp_smem_layout_bytes<NSPLIT, NG, CG>();
-  auto kernel = mlp_umma_kernel<NSPLIT, NG, CG>;
+  auto kernel = mlp_umma_kernel<NSPLIT, NG, CG, ENC>;
+  const EncodeParams enc = encp ? *encp : EncodeParams{};
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
@@ -1005,7 +1104,7 @@ static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, co
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(grid));
-  cfg.blockDim = dim3(kMlpThreads);
+  cfg.blockDim = dim3(ENC ? kMlpEncThreads : kMlpThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1015,7 +1114,7 @@ static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, co
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, trace);
+  return cudaLaunchKernelEx(&cfg, kernel, prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, trace, enc);
 }
 
 template <int CG>
@@ -1051,9 +1150,15 @@ static cudaError_t launch_hp_t(const MlpProgram& prog, const uint8_t* wblob, con
   return cudaLaunchKernelEx(&cfg, kernel, prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, trace);
 }
 
+size_t mlp_enc_scratch_bytes(int num_sms) { return size_t(num_sms) * 2 * 2 * (2 * kBlkBytes); }
+
 cudaError_t launch_mlp(int nsplit, int ng, int cg, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host, int* err_flag,
-                       int num_sms, cudaStream_t stream, long long* trace) {
+                       int num_sms, cudaStream_t stream, long long* trace, const EncodeParams* enc) {
+  if (enc) {   // shading net with the fused input encoder (CTA pairs only)
+    if (nsplit != 1 || cg != 2) return cudaErrorInvalidValue;
+    return launch_mlp_t<1, 2, 2, true>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace, enc);
+  }
   // split precision (sampling net): half-pipelined single-tile kernel; weights packed N-half outermost
   if (nsplit == 2) {
     if (cg == 2) return launch_hp_t<2>(prog, wblob, in_tiles, out, rows_dev, rows_host, err_flag, num_sms, stream, trace);

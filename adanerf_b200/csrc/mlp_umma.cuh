@@ -71,10 +71,29 @@ struct InputLayout {
 };
 
 
+// Fused input encoder of the shading MLP (stage 3 inside the kernel): one extra warp computes the positional
+// encoding of every packed sample (RayMarchFromPoses.batch, src/features.py:458-479) straight into the tile slot's
+// input block, so the [M, 90] feature tensor never exists in HBM.  ray_idx == nullptr: dense mode (ray = sample / K,
+// z = zlut_dense[sample % K]).
+struct EncodeParams {
+  const float* ray_o = nullptr;       // [N,3]
+  const float* ray_d = nullptr;       // [N,3] (un-normalised, as SpherePosDir hands it on)
+  const int32_t* ray_idx = nullptr;   // [M] packed sample -> ray
+  const float* z = nullptr;           // [M] world depth of the packed samples
+  const float* zlut_dense = nullptr;  // [K]
+  int K = 1;
+  float c[3] = {0.f, 0.f, 0.f};       // view_cell_center
+  float sqrt_max_depth = 1.0f;
+  uint8_t* scratch = nullptr;         // grid x 2 slots x 2 buffers x [P | V] blocks of 16 KB (mlp_enc_scratch_bytes)
+};
+size_t mlp_enc_scratch_bytes(int num_sms);
+constexpr int kMlpEncThreads = kMlpThreads + 32;   // + 1 encoder warp (20 warps = 5 per SM sub-partition: still 96 registers)
+
 // Launchers (defined in mlp_umma.cu).  rows_dev may be null (then rows_host is used).
 cudaError_t launch_mlp(int nsplit, int ng, int cg, const MlpProgram& prog, const uint8_t* wblob,
                        const uint8_t* in_tiles, float* out, const long long* rows_dev, long long rows_host,
-                       int* err_flag, int num_sms, cudaStream_t stream, long long* trace = nullptr);
+                       int* err_flag, int num_sms, cudaStream_t stream, long long* trace = nullptr,
+                       const EncodeParams* enc = nullptr);
 cudaError_t launch_pack_rows(const float* x, long long rows, const long long* rows_dev, int n_feat,
                              const InputLayout& lay, uint8_t* tiles, cudaStream_t stream);
 

@@ -106,6 +106,8 @@ adn_status adn_probe_export_dir(const char* dir, adn_scene* scene_out, float* th
 /* name: "chunk_rays" (rays per internal batch, 0 = auto), "profile" (0/1 per-stage event timing),
  * "mlp0_terms" (3 = bf16x3 split precision [default], 1 = plain bf16; parity experiments only),
  * "cta_group" (2 = CTA-pair MMAs [default], 1 = single-CTA MMAs; A/B runs),
+ * "fuse_encoder" (1 = positional encoding of the samples inside the shading kernel: no [M,90]-sized tile buffer, ~5 %
+ *   slower; 0 = separate kernel [default]),
  * "trace" (debug: net id whose MLP kernel records an in-kernel timeline, -1 = off; profiles/trace_mlp.py). */
 adn_status adn_set_option(adn_ctx* ctx, const char* name, int64_t value);
 adn_status adn_get_stats(adn_ctx* ctx, adn_stats* out);   /* synchronises the context's stream */

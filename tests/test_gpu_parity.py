@@ -561,3 +561,22 @@ def test_render_k32_uses_the_general_kernels():
         print(f"K={K} thr={thr}: mean spr {ref['n_samples'].float().mean():.2f}, identical counts {same:.4f}, PSNR {p:.2f} dB")
         assert same >= 0.995 and p > 45.0
     r.close()
+
+
+def test_fused_input_encoder_option():
+    """"fuse_encoder": stage 3 computed by an encoder warp inside the shading kernel (same device functions, the packed
+    bf16 image goes through an L2-resident scratch instead of the [M, 90]-sized tile buffer) -- same picture, bit for bit,
+    adaptive and dense."""
+    scene = orc.SCENE_BARBERSHOP
+    sd0, sd1 = orc.make_weights("shaped", seed=0)
+    r = _renderer(scene, sd0, sd1)
+    pose, rot = torch.tensor(scene["view_cell_center"]), orc.rotation_yaw(45.0)
+    a = r.render_camera(pose, rot, 800, 800, 0.2, 8, row0=100, rows=300, want_nsamples=True)
+    d = r.render_camera(pose, rot, 800, 800, 0.0, 128, row0=0, rows=6)
+    r.set_option("fuse_encoder", 1)
+    b = r.render_camera(pose, rot, 800, 800, 0.2, 8, row0=100, rows=300, want_nsamples=True)
+    e = r.render_camera(pose, rot, 800, 800, 0.0, 128, row0=0, rows=6)
+    r.set_option("fuse_encoder", 0)
+    assert torch.equal(a["n_samples"], b["n_samples"]) and torch.equal(a["rgb"], b["rgb"])
+    assert torch.equal(d["rgb"], e["rgb"])
+    r.close()
