@@ -55,8 +55,9 @@ def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full summary (None when absent)."""
     p = os.path.join(ROOT, "profiles", "ncu_r1_summary.json")
     try:
-        d = json.load(open(p))[kernel]
-        return int(d["dram_rd"] + d["dram_wr"])
+        table = json.load(open(p))
+        key = kernel if kernel in table else next(k for k in table if k.startswith(kernel.rstrip(">")))   # trailing template args
+        return int(table[key]["dram_rd"] + table[key]["dram_wr"])
     except Exception:
         return None
 
