@@ -253,7 +253,7 @@ adn_status build_net0(adn_ctx* ctx) {
     L.n_kb = uint8_t(segs.size());
     for (size_t i = 0; i < segs.size(); ++i) L.a_blk[i] = uint8_t(i);
     L.n_half = uint8_t(n_out / 128);
-    L.flags = last ? LF_FINAL_RAW : uint8_t(LF_RELU | LF_OUT_ACT);
+    L.flags = last ? uint8_t(LF_FINAL_RAW) : uint8_t(LF_RELU | LF_OUT_ACT);
     L.out_blk0 = 0;
     L.w_off = uint32_t(wblob.size());
     pack_layer(W->data.data(), n_out, k_in, segs, nsplit, wblob);
