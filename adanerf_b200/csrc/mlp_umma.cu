@@ -683,7 +683,10 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
             if (QW > 1) {
               float4* scratch = reinterpret_cast<float4*>(act_ptr(g, 0, prog.hid_blk0));
               if (sub > 0) scratch[(sub - 1) * kTileM + row_in_tile] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
-              named_bar_sync(1, EW * 32);
+              // only the QW warps of this lane quarter exchange rows (ids 12..15).  No barrier after the reads: the next
+              // writer of these blocks is the next tile's layer-0 epilogue, which cannot start before ALL epilogue warps
+              // -- the readers included -- have arrived on act_ready.
+              named_bar_sync(12 + quarter, QW * 32);
               if (sub == 0) {
 #pragma unroll
                 for (int q = 1; q < QW; ++q) {
@@ -694,7 +697,6 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
                   alpha += p.w;
                 }
               }
-              named_bar_sync(1, EW * 32);
             }
             if (sub == 0 && grow < rows) {
               const float ab = prog.side[prog.alpha_b_off];
