@@ -414,7 +414,7 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
 //   * picks are emitted in ascending cell order (rank = popcount of the selection mask below the cell) into a
 //     shared staging area that aliases the dead rows, then copied out coalesced after the tile's look-back scan.
 constexpr int kS2tRowBytes = 528;
-constexpr int kS2tGmBytes = 80;
+constexpr int kS2tGmBytes = 0;    // group maxima live in registers
 constexpr size_t kS2tSmemBytes = size_t(kS2Rays) * (kS2tRowBytes + kS2tGmBytes) + 128 * sizeof(float);
 
 template <int KMAX>
@@ -462,20 +462,12 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
 
   const float NEG = __int_as_float(0xff800000);
   const float4* row4 = reinterpret_cast<const float4*>(row);
-  float4* gm4 = reinterpret_cast<float4*>(gms + tid * kS2tGmBytes);
-  float* gm = reinterpret_cast<float*>(gm4);
   auto max8 = [](const float4 a, const float4 b) {
     return fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
   };
+  float g[16];   // group maxima, registers
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float4 g;
-    g.x = max8(row4[8 * q + 0], row4[8 * q + 1]);
-    g.y = max8(row4[8 * q + 2], row4[8 * q + 3]);
-    g.z = max8(row4[8 * q + 4], row4[8 * q + 5]);
-    g.w = max8(row4[8 * q + 6], row4[8 * q + 7]);
-    gm4[q] = g;
-  }
+  for (int q = 0; q < 16; ++q) g[q] = max8(row4[2 * q], row4[2 * q + 1]);
 
   uint32_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;   // selection mask over the 128 cells
   float mv[KMAX];                                 // popped values, pick order
@@ -489,15 +481,6 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
     mv[j] = 0.0f;
     if (j >= K) break;                                        // warp uniform
     if (!__any_sync(0xffffffffu, active)) break;              // warp uniform
-    float g[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 t = gm4[q];
-      g[4 * q + 0] = t.x;
-      g[4 * q + 1] = t.y;
-      g[4 * q + 2] = t.z;
-      g[4 * q + 3] = t.w;
-    }
     const float m = fmaxf(fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]))),
                           fmaxf(fmaxf(fmaxf(g[8], g[9]), fmaxf(g[10], g[11])), fmaxf(fmaxf(g[12], g[13]), fmaxf(g[14], g[15]))));
     int gi = 0;
@@ -517,7 +500,8 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
       nm = fmaxf(nm, e ? NEG : x[i]);          // the group's maximum once that cell is gone
     }
     grp[idx] = NEG;
-    gm[gi] = nm;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] = (i == gi) ? nm : g[i];
     const bool sel = active && (j == 0 || m >= thr);
     active = sel;
     const int cell = 8 * gi + idx;
