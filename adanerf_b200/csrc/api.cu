@@ -63,6 +63,7 @@ struct adn_ctx {
   long long* d_trace = nullptr;   // debug timeline of the MLP kernels (option "trace")
   int trace_net = -1;
   // pinned staging for the *_host entry points
+  Stage2Sync s2sync;              // epoch / ticket base of s2scratch (no per-launch memset)
   Buf h_in, h_out, h_ns;
   // caller buffers page-locked in place (cudaHostRegister) so repeated calls DMA straight from / to them
   struct Reg { const void* p = nullptr; size_t bytes = 0; const void* last_seen = nullptr; };
@@ -528,7 +529,7 @@ adn_status render_chunk(adn_ctx* ctx, const PoseDev& pd, const float* d_dirs, co
   } else {
     ADN_CUDA(ctx, launch_stage2(raw0, n, thr, K, ctx->d_zlut, count, offset, nullptr, static_cast<int32_t*>(ctx->rayidx.p),
                                 static_cast<float*>(ctx->zbuf.p), static_cast<float*>(ctx->zpbuf.p), ctx->d_total,
-                                ctx->s2scratch.p, st));
+                                ctx->s2scratch.p, &ctx->s2sync, st));
   }
   ctx->stats.kernel_launches++;
   if (timing) cudaEventRecord(ctx->ev[3], st);
@@ -958,7 +959,7 @@ adn_status adn_stage2_sample(adn_ctx* ctx, const float* d_raw0, int64_t n_rays, 
   adn_status s = ensure(ctx, ctx->s2scratch, stage2_scratch_bytes(n_rays));
   if (s != ADN_OK) return s;
   ADN_CUDA(ctx, launch_stage2(d_raw0, n_rays, thr, K, ctx->d_zlut, d_count, d_offset, d_cell, d_ray, d_z, d_zp,
-                              reinterpret_cast<long long*>(d_total), ctx->s2scratch.p, static_cast<cudaStream_t>(stream)));
+                              reinterpret_cast<long long*>(d_total), ctx->s2scratch.p, &ctx->s2sync, static_cast<cudaStream_t>(stream)));
   ctx->stats.kernel_launches++;
   return ADN_OK;
 }

@@ -248,12 +248,24 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 
 // Tile bookkeeping, executed by one full warp.  Tiles are numbered by dynamic tickets, so every predecessor a tile
 // spins on has already started.  A tile's state word carries flag and value together (no fence needed).
-constexpr unsigned long long kS2FlagAgg = 1ull << 62, kS2FlagInc = 2ull << 62, kS2ValMask = (1ull << 62) - 1;
+// State word: [63:62] flag (1 = tile aggregate, 2 = inclusive prefix), [61:40] launch epoch, [39:0] value.  A word whose
+// epoch is not the current launch's reads as "not ready", so the state array is never cleared between launches
+// (launch_stage2 zeroes it when the buffer is new and when the 22-bit epoch wraps); tickets are consumed relative to a
+// per-launch base for the same reason.
+constexpr unsigned long long kS2FlagAgg = 1ull << 62, kS2FlagInc = 2ull << 62, kS2ValMask = (1ull << 40) - 1;
+constexpr uint32_t kS2EpochMask = (1u << 22) - 1;
+__device__ __forceinline__ unsigned long long s2_pack(unsigned long long flag, uint32_t epoch, long long value) {
+  return flag | ((unsigned long long)epoch << 40) | ((unsigned long long)value & kS2ValMask);
+}
+// flag of a state word as seen by launch `epoch` (0 = not ready / stale)
+__device__ __forceinline__ uint32_t s2_flag(unsigned long long st, uint32_t epoch) {
+  return (uint32_t(st >> 40) & kS2EpochMask) == epoch ? uint32_t(st >> 62) : 0u;
+}
 
 // Exclusive scan of the tile's 64 per-ray counts (-> s_off); publishes the tile aggregate right away so that the
 // successors' look-backs can pass over this tile while it is still busy.  Returns the tile total.
 __device__ __forceinline__ int s2_tile_scan(const int* s_cnt, int* s_off, int tile, int lane,
-                                            unsigned long long* __restrict__ tile_state) {
+                                            unsigned long long* __restrict__ tile_state, uint32_t epoch) {
   const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
   int x = a + b;
 #pragma unroll
@@ -265,7 +277,7 @@ __device__ __forceinline__ int s2_tile_scan(const int* s_cnt, int* s_off, int ti
   s_off[2 * lane] = excl;
   s_off[2 * lane + 1] = excl + a;
   const int tile_total = __shfl_sync(0xffffffffu, x, 31);
-  if (tile > 0 && lane == 0) atomicExch(&tile_state[tile], kS2FlagAgg | (unsigned long long)tile_total);
+  if (tile > 0 && lane == 0) atomicExch(&tile_state[tile], s2_pack(kS2FlagAgg, epoch, tile_total));
   return tile_total;
 }
 
@@ -274,7 +286,8 @@ __device__ __forceinline__ int s2_tile_scan(const int* s_cnt, int* s_off, int ti
 // that chain is the kernel's critical path: the window is 128 tiles (4 independent loads per lane in flight) so
 // the chain is ~80 hops instead of ~320.
 __device__ __forceinline__ void s2_lookback(long long* s_prefix, int tile, int tile_total, int n_tiles, int lane,
-                                            unsigned long long* __restrict__ tile_state, long long* __restrict__ total) {
+                                            unsigned long long* __restrict__ tile_state, long long* __restrict__ total,
+                                            uint32_t epoch) {
   long long prefix = 0;
   if (tile > 0) {
     int idx = tile - 1;   // nearest predecessor not yet accounted for
@@ -285,15 +298,16 @@ __device__ __forceinline__ void s2_lookback(long long* s_prefix, int tile, int t
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int my = idx - 32 * k - lane;
-        st[k] = (my >= 0) ? ld_volatile_u64(&tile_state[my]) : kS2FlagInc;   // virtual predecessor of tile 0: prefix 0
+        st[k] = (my >= 0) ? ld_volatile_u64(&tile_state[my]) : s2_pack(kS2FlagInc, epoch, 0);   // virtual predecessor of tile 0
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (done) break;
         int first_inc;
         while (true) {
-          const uint32_t ready = __ballot_sync(0xffffffffu, (st[k] >> 62) != 0);
-          const uint32_t inc = __ballot_sync(0xffffffffu, (st[k] >> 62) == 2);
+          const uint32_t fl = s2_flag(st[k], epoch);
+          const uint32_t ready = __ballot_sync(0xffffffffu, fl != 0);
+          const uint32_t inc = __ballot_sync(0xffffffffu, fl == 2);
           first_inc = inc ? (__ffs(inc) - 1) : 32;   // lanes [0, first_inc] must all be ready
           const uint32_t need = (first_inc >= 31) ? 0xffffffffu : ((2u << first_inc) - 1u);
           if ((ready & need) == need) break;
@@ -311,7 +325,7 @@ __device__ __forceinline__ void s2_lookback(long long* s_prefix, int tile, int t
     }
   }
   if (lane == 0) {
-    atomicExch(&tile_state[tile], kS2FlagInc | (unsigned long long)(prefix + tile_total));
+    atomicExch(&tile_state[tile], s2_pack(kS2FlagInc, epoch, prefix + tile_total));
     *s_prefix = prefix;
     if (tile == n_tiles - 1) *total = prefix + tile_total;
   }
@@ -322,7 +336,7 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
               int32_t* __restrict__ count, int32_t* __restrict__ offset, int32_t* __restrict__ cell_out,
               int32_t* __restrict__ ray_out, float* __restrict__ z_out, float* __restrict__ zp_out,
               long long* __restrict__ total, unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
-              int n_tiles) {
+              int n_tiles, uint32_t epoch, uint32_t ticket_base) {
   __shared__ uint32_t s_sel[kS2Rays][4];
   __shared__ int s_cnt[kS2Rays];
   __shared__ int s_off[kS2Rays];
@@ -330,7 +344,7 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
   __shared__ int s_tile;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) s_tile = int(atomicAdd(ticket, 1u));
+  if (threadIdx.x == 0) s_tile = int(atomicAdd(ticket, 1u) - ticket_base);
   __syncthreads();
   const int tile = s_tile;
   const long long ray0 = (long long)tile * kS2Rays;
@@ -359,8 +373,8 @@ stage2_kernel(const float* __restrict__ raw0, long long n_rays, float thr, int K
 
   // CTA scan + decoupled look-back (warp 0)
   if (warp == 0) {
-    const int tile_total = s2_tile_scan(s_cnt, s_off, tile, lane, tile_state);
-    s2_lookback(&s_prefix, tile, tile_total, n_tiles, lane, tile_state, total);
+    const int tile_total = s2_tile_scan(s_cnt, s_off, tile, lane, tile_state, epoch);
+    s2_lookback(&s_prefix, tile, tile_total, n_tiles, lane, tile_state, total, epoch);
   }
   __syncthreads();
   const long long prefix = s_prefix;
@@ -423,7 +437,7 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
                      int32_t* __restrict__ count, int32_t* __restrict__ offset, int32_t* __restrict__ cell_out,
                      int32_t* __restrict__ ray_out, float* __restrict__ z_out, float* __restrict__ zp_out,
                      long long* __restrict__ total, unsigned long long* __restrict__ tile_state,
-                     unsigned int* __restrict__ ticket, int n_tiles) {
+                     unsigned int* __restrict__ ticket, int n_tiles, uint32_t epoch, uint32_t ticket_base) {
   extern __shared__ __align__(16) uint8_t s2t_smem[];
   uint8_t* rows = s2t_smem;
   uint8_t* gms = rows + kS2Rays * kS2tRowBytes;
@@ -434,7 +448,7 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
   __shared__ int s_tile;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) s_tile = int(atomicAdd(ticket, 1u));
+  if (tid == 0) s_tile = int(atomicAdd(ticket, 1u) - ticket_base);
   __syncthreads();
   const int tile = s_tile;
   const long long ray0 = (long long)tile * kS2Rays;
@@ -519,7 +533,7 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
   s_cnt[tid] = cnt;
   __syncthreads();   // every thread is done with its row: the row area becomes the staging area
   int tile_total_w0 = 0;
-  if (warp == 0) tile_total_w0 = s2_tile_scan(s_cnt, s_off, tile, lane, tile_state);
+  if (warp == 0) tile_total_w0 = s2_tile_scan(s_cnt, s_off, tile, lane, tile_state, epoch);
   __syncthreads();
   const int off = s_off[tid];
 
@@ -543,7 +557,7 @@ stage2_thread_kernel(const float* __restrict__ raw0, long long n_rays, float thr
     }
   }
   // the look-back (a chain of L2 round trips) starts only after this warp's own staging work is out of the way
-  if (warp == 0) s2_lookback(&s_prefix, tile, tile_total_w0, n_tiles, lane, tile_state, total);
+  if (warp == 0) s2_lookback(&s_prefix, tile, tile_total_w0, n_tiles, lane, tile_state, total, epoch);
   __syncthreads();
   const long long prefix = s_prefix;
   if (valid) {
@@ -567,24 +581,35 @@ size_t stage2_scratch_bytes(long long n_rays) {
 
 cudaError_t launch_stage2(const float* d_raw0, long long n_rays, float thr, int K, const float* d_zlut, int32_t* d_count,
                           int32_t* d_offset, int32_t* d_cell, int32_t* d_ray, float* d_z, float* d_zp, long long* d_total,
-                          void* d_scratch, cudaStream_t s) {
+                          void* d_scratch, Stage2Sync* sync, cudaStream_t s) {
   if (n_rays <= 0) return cudaMemsetAsync(d_total, 0, sizeof(long long), s);
   const int n_tiles = int((n_rays + kS2Rays - 1) / kS2Rays);
-  cudaError_t e = cudaMemsetAsync(d_scratch, 0, stage2_scratch_bytes(n_rays), s);
-  if (e != cudaSuccess) return e;
-  unsigned long long* state = reinterpret_cast<unsigned long long*>(d_scratch);
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(state + n_tiles);
-  // thread-per-ray kernel whenever its assumptions hold (K <= 16, 16-byte aligned rows for the bulk copies)
+  const size_t bytes = stage2_scratch_bytes(n_rays);
+  // [ticket | states]: cleared only when the buffer is new / has grown or the epoch wraps (see the state-word comment)
+  sync->epoch = (sync->epoch + 1) & kS2EpochMask;
+  if (sync->scratch != d_scratch || sync->cleared_bytes < bytes || sync->epoch == 0) {
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, bytes, s);
+    if (e != cudaSuccess) return e;
+    sync->scratch = d_scratch;
+    sync->cleared_bytes = bytes;
+    sync->epoch = 1;
+    sync->ticket_base = 0;
+  }
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(d_scratch);
+  unsigned long long* state = reinterpret_cast<unsigned long long*>(d_scratch) + 1;
+  const uint32_t epoch = sync->epoch, base = sync->ticket_base;
+  sync->ticket_base += uint32_t(n_tiles);   // the launch consumes exactly n_tiles tickets (unsigned wrap-around is fine)
+  // thread-per-ray kernel whenever its assumptions hold (K <= 16, 16-byte aligned rows for the cp.async fetch)
   const bool aligned = (reinterpret_cast<uintptr_t>(d_raw0) & 15u) == 0;
   if (K <= 8 && aligned)
     stage2_thread_kernel<8><<<n_tiles, kS2Rays, kS2tSmemBytes, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray,
-                                                                   d_z, d_zp, d_total, state, ticket, n_tiles);
+                                                                   d_z, d_zp, d_total, state, ticket, n_tiles, epoch, base);
   else if (K <= 16 && aligned)
     stage2_thread_kernel<16><<<n_tiles, kS2Rays, kS2tSmemBytes, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray,
-                                                                    d_z, d_zp, d_total, state, ticket, n_tiles);
+                                                                    d_z, d_zp, d_total, state, ticket, n_tiles, epoch, base);
   else
     stage2_kernel<<<n_tiles, kS2Threads, 0, s>>>(d_raw0, n_rays, thr, K, d_zlut, d_count, d_offset, d_cell, d_ray, d_z, d_zp,
-                                               d_total, state, ticket, n_tiles);
+                                                 d_total, state, ticket, n_tiles, epoch, base);
   return cudaGetLastError();
 }
 

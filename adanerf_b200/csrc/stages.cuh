@@ -35,9 +35,16 @@ cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_
 
 // Stage 2.  tile_state: [n_ctas + 2] uint64 scratch zeroed by the launcher (memsetAsync).
 size_t stage2_scratch_bytes(long long n_rays);
-cudaError_t launch_stage2(const float* d_raw0, long long n_rays, float thr, int K, const float* d_zlut,
-                          int32_t* d_count, int32_t* d_offset, int32_t* d_cell, int32_t* d_ray, float* d_z, float* d_zp,
-                          long long* d_total, void* d_scratch, cudaStream_t s);
+// Host-side bookkeeping of a stage-2 scratch buffer (owned by whoever owns the buffer): launch epoch and ticket base, so
+// the tile states / ticket counter need no per-launch memset.
+struct Stage2Sync {
+  void* scratch = nullptr;
+  size_t cleared_bytes = 0;
+  uint32_t epoch = 0, ticket_base = 0;
+};
+cudaError_t launch_stage2(const float* d_raw0, long long n_rays, float thr, int K, const float* d_zlut, int32_t* d_count,
+                          int32_t* d_offset, int32_t* d_cell, int32_t* d_ray, float* d_z, float* d_zp, long long* d_total,
+                          void* d_scratch, Stage2Sync* sync, cudaStream_t s);
 // Dense (thr == 0): count = K, offset = ray*K, total = N*K; no index arrays are materialised.
 cudaError_t launch_stage2_dense(long long n_rays, int K, int32_t* d_count, int32_t* d_offset, long long* d_total,
                                 cudaStream_t s);
