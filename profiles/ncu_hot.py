@@ -1,8 +1,13 @@
-"""Prints headline metrics and the hottest SASS instructions (by stall samples) of one kernel in an .ncu-rep."""
+"""Prints headline metrics and the hottest SASS instructions (by stall samples) of one kernel in an .ncu-rep.
+    python profiles/ncu_hot.py report.ncu-rep [min %% of samples] [regex:kernel]"""
 import csv, subprocess, sys, io
 
+KERNEL = sys.argv[3] if len(sys.argv) > 3 else None   # e.g. regex:stage2_thread
+
+
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", name, "--csv"] + (["--kernel-name", KERNEL] if KERNEL else [])
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 def main():
