@@ -27,7 +27,7 @@ def main():
     st = [(float(v[i].replace(",", "")), h) for i, h in enumerate(hdr) if h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("not_issued")]
     tot = sum(x for x, _ in st)
     print("stall samples:", ", ".join(f"{h.split('stalled_')[1]} {100 * x / tot:.0f}%" for x, h in sorted(st, reverse=True)[:8]))
-    src = page(rep, "source")[2:]
+    src = [r for r in page(rep, "source")[2:] if len(r) > 5 and r[4].strip().isdigit()]
     tot = sum(int(r[4]) for r in src) or 1
     acc = 0
     thr = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
