@@ -199,6 +199,19 @@ size_t push_floats(std::vector<float>& f, const float* src, size_t n) {
   return off;
 }
 
+// Bias vector of a layer: fp32, or -- hidden layers of plain-bf16 nets -- bf16 pairs (element 2i in the low half of word i),
+// which the epilogue unpacks with a shift / mask (see epilogue_chunk).  Returns the word offset in `f`.
+size_t push_bias(std::vector<float>& f, const float* b, size_t n, bool packed_bf16) {
+  if (!packed_bf16) return push_floats(f, b, n);
+  std::vector<float> words((n + 1) / 2);
+  for (size_t i = 0; i < words.size(); ++i) {
+    const uint32_t lo = f2bf(b[2 * i]), hi = (2 * i + 1 < n) ? f2bf(b[2 * i + 1]) : 0u;
+    const uint32_t w = lo | (hi << 16);
+    std::memcpy(&words[i], &w, 4);
+  }
+  return push_floats(f, words.data(), words.size());
+}
+
 const HostTensor* find(const Net& n, const std::string& name) {
   auto it = n.tensors.find(name);
   return it == n.tensors.end() ? nullptr : &it->second;
@@ -258,7 +271,7 @@ adn_status build_net0(adn_ctx* ctx) {
     L.out_blk0 = 0;
     L.w_off = uint32_t(wblob.size());
     pack_layer(W->data.data(), n_out, k_in, segs, nsplit, wblob);
-    L.bias_off = uint32_t(push_floats(fblob, B->data.data(), B->data.size()));
+    L.bias_off = uint32_t(push_bias(fblob, B->data.data(), B->data.size(), nsplit == 1 && !last));
     if (last) {
       net.n_out = n_out;
       P.out_cols = n_out;
@@ -373,7 +386,8 @@ adn_status build_net1(adn_ctx* ctx) {
     L.n_kb = uint8_t(segs.size());
     L.w_off = uint32_t(wblob.size());
     pack_layer(W->data.data(), int(W->rows), int(W->cols), segs, 1, wblob);
-    L.bias_off = uint32_t(push_floats(fblob, B->data.data(), B->data.size()));
+    // hidden layers (activation-writing epilogues): bf16 pairs; the last layer (rgb head epilogue): fp32
+    L.bias_off = uint32_t(push_bias(fblob, B->data.data(), B->data.size(), !(L.flags & LF_FINAL_RGB)));
   }
   P.alpha_w_off = uint32_t(push_floats(fblob, aw->data.data(), 256));
   P.alpha_b_off = uint32_t(push_floats(fblob, ab->data.data(), 1));
