@@ -1105,14 +1105,13 @@ template <int NSPLIT, int NG, int CG, bool ENC = false>
 static cudaError_t launch_mlp_t(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles,
                                 float* out, const long long* rows_dev, long long rows_host, int* err_flag, int num_sms,
                                 cudaStream_t stream, long long* trace, const EncodeParams* encp = nullptr) {
-  static bool attr_set = false;
+  static unsigned long long attr_done = 0;   // per device (the attribute is per device)
   const size_t smem = mlp_smem_layout_bytes<NSPLIT, NG, CG>();
   auto kernel = mlp_umma_kernel<NSPLIT, NG, CG, ENC>;
   const EncodeParams enc = encp ? *encp : EncodeParams{};
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  {
+    cudaError_t e = set_max_dyn_smem_once(reinterpret_cast<const void*>(kernel), int(smem), &attr_done);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   int grid = (num_sms / CG) * CG;   // persistent: one CTA (or CTA pair) per SM (pair)
   if (!rows_dev) {
@@ -1139,13 +1138,12 @@ template <int CG>
 static cudaError_t launch_hp_t(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles, float* out,
                                const long long* rows_dev, long long rows_host, int* err_flag, int num_sms, cudaStream_t stream,
                                long long* trace) {
-  static bool attr_set = false;
+  static unsigned long long attr_done = 0;
   const size_t smem = mlp_smem_layout_bytes<2, 1, CG>();
   auto kernel = mlp_hp_kernel<CG>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  {
+    cudaError_t e = set_max_dyn_smem_once(reinterpret_cast<const void*>(kernel), int(smem), &attr_done);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   int grid = (num_sms / CG) * CG;
   if (!rows_dev) {

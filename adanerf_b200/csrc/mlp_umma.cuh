@@ -21,7 +21,16 @@ constexpr int kTileM = 128;
 constexpr int kBlkBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B block
 constexpr int kMaxLayers = 12;
 constexpr int kMlpThreads = 608;  // 19 warps: 16 epilogue, weight producer, barrier helper, MMA issuer
-constexpr int kSideFloats = 3200; // fp32 side parameters (biases, alpha / rgb heads) carried in the kernel parameters
+constexpr int kSideFloats = 3208; // fp32 side parameters (biases, alpha / rgb heads) carried in the kernel parameters
+
+// Fixed side-parameter layout of the shading net for mlp_sh_kernel (mlp_sh.cu): every epilogue is specialised per layer,
+// so its bias / head constants are compile-time offsets into MlpProgram::side and reach the FADD / FFMA as immediate
+// constant-bank operands (no load instruction at all).  Layer l's fp32 bias: [256 l, 256 l + n_out).
+constexpr int kShLayers = 10;
+constexpr int kShAlphaW = 2560;   // alpha_linear.weight [256]
+constexpr int kShRgbW = 2816;     // rgb_linear.weight [3][128]
+constexpr int kShAlphaB = 3200;   // alpha_linear.bias
+constexpr int kShRgbB = 3201;     // rgb_linear.bias [3]
 
 enum : uint8_t {
   LF_RELU = 1,
@@ -41,7 +50,9 @@ struct MlpLayer {
   uint8_t n_half;     // N / 128  (1 or 2)
   uint8_t flags;
   uint8_t out_blk0;   // first activation block the epilogue writes
-  uint8_t pad[2];
+  // mlp_sh_kernel: the (N half, stage) of this layer after whose MMAs the blocks that half 0's epilogue overwrites in
+  // place (out_blk0, out_blk0 + 1) are no longer read -- the issuer commits `lo_free` there.  0xFF: not used.
+  uint8_t lo_h, lo_s;
 };
 
 struct MlpProgram {
@@ -54,6 +65,16 @@ struct MlpProgram {
   uint32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;  // float offsets in `side`
   int32_t out_cols;           // row stride of the FINAL_RAW output
   MlpLayer layers[kMaxLayers];
+  // mlp_sh_kernel: the issue schedule, one word per (layer, N half, stage) step in issue order, precomputed on the host so
+  // that the MMA issuer and the dependency helper decode instead of deriving it (the issuer's instruction count per
+  // 8-MMA group is the kernel's clock).  Bits: 0-3 / 4-7 activation block of K block 2s / 2s+1; 8 stage holds two K
+  // blocks; 9-10 dependencies a slot picks up here for the first time in this layer (9: previous layer's half-0 epilogue,
+  // 10: half-1 epilogue); 12 commit acc_full after this step; 13 commit lo_free; 14 N half; 15 first step of the half
+  // (accumulator is overwritten, not accumulated); 16 the step's K block is the tile input (positions / view block), an
+  // A operand that travels through the weight ring; 17 it is fetched at this step (two ring stages, one per slot, after
+  // the weight stage); 18 released after this step; 19 it is the view block (two K steps); 20-21 stage index in the half.
+  uint32_t sh_sched[kMaxLayers][6];
+  uint8_t sh_steps[kMaxLayers];
   // Biases and the two tiny heads live in the kernel parameter (constant) bank: every lane of a warp reads
   // the same column's value, so the epilogue gets them through uniform constant loads, not the LSU.
   float side[kSideFloats];
@@ -88,6 +109,16 @@ struct EncodeParams {
 };
 size_t mlp_enc_scratch_bytes(int num_sms);
 constexpr int kMlpEncThreads = kMlpThreads + 32;   // + 1 encoder warp (20 warps = 5 per SM sub-partition: still 96 registers)
+
+// Shading net on mlp_sh_kernel (mlp_sh.cu): weight-stationary across two tile slots, N-half pipelined, CTA pairs.
+// The program must be the one build_net1 emits in "sh" mode (fixed side layout, weights packed N half outermost).
+cudaError_t launch_mlp_sh(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles, float* out,
+                          const long long* rows_dev, long long rows_host, int* err_flag, int num_sms, cudaStream_t stream,
+                          long long* trace = nullptr);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device).
+// `done` is the caller's per-kernel bit mask (one static per launcher).
+cudaError_t set_max_dyn_smem_once(const void* func, int bytes, unsigned long long* done);
 
 // Launchers (defined in mlp_umma.cu).  rows_dev may be null (then rows_host is used).
 cudaError_t launch_mlp(int nsplit, int ng, int cg, const MlpProgram& prog, const uint8_t* wblob,

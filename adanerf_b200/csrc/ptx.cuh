@@ -21,6 +21,12 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // Named CTA barriers (bar.sync / bar.arrive with an explicit participant count).
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -88,6 +94,42 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int site) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, err_flag, site);
+}
+// Polling variant (mbarrier.test_wait, no hardware suspend): lower wake-up latency, costs issue slots while waiting.
+static __device__ __noinline__ void mbar_spin_slow(uint64_t* bar, uint32_t parity, int* err_flag, int site) {
+  const long long t0 = clock64();
+  while (!mbar_test(bar, parity)) {
+    if (clock64() - t0 > ADN_WATCHDOG_CYCLES) {
+      if (err_flag) atomicExch(err_flag, 0x1000 + site);
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int* err_flag, int site) {
+  if (mbar_test(bar, parity)) return;
+  mbar_spin_slow(bar, parity, err_flag, site);
+}
+
+// Warp-convergent wait on ONE MBARRIER PER LANE: every lane with `mine` set names its own barrier / parity, the warp
+// returns when all of them have completed.  Each iteration issues a single try_wait for all participating lanes
+// (divergent per-lane mbar_wait calls would be executed one lane after the other, ~200 cycles each).
+#ifndef ADN_SPIN_ISSUER
+#define ADN_SPIN_ISSUER 0   // 1: the issuer / forwarder warps poll with test_wait (no hardware suspend) -- experiment
+#endif
+__device__ __forceinline__ void mbar_wait_lanes(uint64_t* bar, uint32_t parity, bool mine, int* err_flag, int site) {
+  bool ok = !mine;
+  if (__all_sync(0xffffffffu, ok)) return;   // nothing to wait for (the early probe has seen it complete)
+  const long long t0 = clock64();
+  for (;;) {
+    if (!ok) ok = ADN_SPIN_ISSUER ? mbar_test(bar, parity) : mbar_try_wait(bar, parity);
+    if (__all_sync(0xffffffffu, ok)) break;
+    if (clock64() - t0 > ADN_WATCHDOG_CYCLES) {
+      if (err_flag) atomicExch(err_flag, 0x1000 + site);
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
 }
 
 // --------------------------------------------------------------------------- async bulk copy

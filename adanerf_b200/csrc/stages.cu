@@ -147,12 +147,10 @@ cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_
   const unsigned grid = unsigned((n_pad + 127) / 128);
   CameraRays c{};
   const size_t smem = d_tiles0 ? size_t(4 * kBlkBytes) : 0;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(stage0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kBlkBytes);
-    cudaFuncSetAttribute(stage0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kBlkBytes);
-    attr = true;
-  }
+  static unsigned long long attr_cam = 0, attr_rays = 0;   // per device
+  if (set_max_dyn_smem_once(reinterpret_cast<const void*>(stage0_kernel<true>), 4 * kBlkBytes, &attr_cam) != cudaSuccess ||
+      set_max_dyn_smem_once(reinterpret_cast<const void*>(stage0_kernel<false>), 4 * kBlkBytes, &attr_rays) != cudaSuccess)
+    return cudaGetLastError();
   if (cam) c = *cam;
   if (sc.n_freq_pos0 == 2 && sc.n_freq_dir0 == 2) {   // "2-2": fp32 rows only (the generic pack kernel builds the tiles)
     if (d_tiles0) return cudaErrorInvalidValue;
@@ -737,11 +735,8 @@ cudaError_t launch_stage3(const SceneDev& sc, const float* d_ray_o, const float*
   long long blocks = (n_samples + kTileM - 1) / kTileM;
   const long long cap = 148ll * 64;
   if (d_total && blocks > cap) blocks = cap;   // grid-stride when the true count lives on the device
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(stage3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBlkBytes);
-    attr = true;
-  }
+  static unsigned long long attr_done = 0;   // per device
+  if (set_max_dyn_smem_once(reinterpret_cast<const void*>(stage3_kernel), 2 * kBlkBytes, &attr_done) != cudaSuccess) return cudaGetLastError();
   stage3_kernel<<<unsigned(blocks), 128, d_tiles1 ? size_t(2 * kBlkBytes) : 0, s>>>(sc, d_ray_o, d_ray_d, d_ray, d_z, d_zlut_dense, K,
                                                                                       n_samples, d_total, d_x1, d_tiles1);
   return cudaGetLastError();

@@ -566,17 +566,26 @@ def test_render_k32_uses_the_general_kernels():
 def test_fused_input_encoder_option():
     """"fuse_encoder": stage 3 computed by an encoder warp inside the shading kernel (same device functions, the packed
     bf16 image goes through an L2-resident scratch instead of the [M, 90]-sized tile buffer) -- same picture, bit for bit,
-    adaptive and dense."""
+    adaptive and dense.  The encoder warp lives in mlp_umma_kernel<1,2,2> (the round-1 shading kernel, option
+    "shading_kernel" 0), so that kernel is the bit-exact baseline; the default mlp_sh_kernel (fp32 instead of bf16-pair
+    biases) must agree with it to bf16-noise level."""
     scene = orc.SCENE_BARBERSHOP
     sd0, sd1 = orc.make_weights("shaped", seed=0)
     r = _renderer(scene, sd0, sd1)
     pose, rot = torch.tensor(scene["view_cell_center"]), orc.rotation_yaw(45.0)
+    new = r.render_camera(pose, rot, 800, 800, 0.2, 8, row0=100, rows=300, want_nsamples=True)
+    r.set_option("shading_kernel", 0)
     a = r.render_camera(pose, rot, 800, 800, 0.2, 8, row0=100, rows=300, want_nsamples=True)
     d = r.render_camera(pose, rot, 800, 800, 0.0, 128, row0=0, rows=6)
     r.set_option("fuse_encoder", 1)
     b = r.render_camera(pose, rot, 800, 800, 0.2, 8, row0=100, rows=300, want_nsamples=True)
     e = r.render_camera(pose, rot, 800, 800, 0.0, 128, row0=0, rows=6)
     r.set_option("fuse_encoder", 0)
+    r.set_option("shading_kernel", 1)
     assert torch.equal(a["n_samples"], b["n_samples"]) and torch.equal(a["rgb"], b["rgb"])
     assert torch.equal(d["rgb"], e["rgb"])
+    assert torch.equal(a["n_samples"], new["n_samples"])
+    p = orc.psnr(new["rgb"].cpu(), a["rgb"].cpu())
+    print(f"mlp_sh_kernel vs mlp_umma_kernel<1,2,2>: PSNR {p:.1f} dB")
+    assert p > 60.0
     r.close()
