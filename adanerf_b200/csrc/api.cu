@@ -403,45 +403,56 @@ adn_status build_net1(adn_ctx* ctx) {
     }
     L.n_kb = uint8_t(segs.size());
     L.w_off = uint32_t(wblob.size());
-    pack_layer(W->data.data(), int(W->rows), int(W->cols), segs, 1, wblob);
+    pack_layer(W->data.data(), int(W->rows), int(W->cols), segs, 1, wblob, sh);
     if (sh) {
       L.bias_off = uint32_t(256 * l);   // fp32, fixed offset: an immediate operand of the specialised epilogue
       std::memcpy(&fblob[L.bias_off], B->data.data(), B->data.size() * 4);
+      if (L.n_half == 2 && (L.flags & LF_OUT_ACT)) {
+        // last (half, stage) in issue order that reads the blocks half 0's epilogue writes (out_blk0, out_blk0 + 1)
+        L.lo_h = L.lo_s = 0;
+        for (int h = 0; h < 2; ++h)
+          for (int kb = 0; kb < int(L.n_kb); ++kb)
+            if (L.a_blk[kb] == L.out_blk0 || L.a_blk[kb] == L.out_blk0 + 1) {
+              L.lo_h = uint8_t(h);
+              L.lo_s = uint8_t(kb / 2);
+            }
+      }
     } else {
       // hidden layers (activation-writing epilogues): bf16 pairs; the last layer (rgb head epilogue): fp32
       L.bias_off = uint32_t(push_bias(fblob, B->data.data(), B->data.size(), !(L.flags & LF_FINAL_RGB)));
     }
   }
   if (sh) {
-    // issue schedule of mlp_sh_kernel (see MlpProgram::sh_sched): one slot's pass over a layer
+    // issue schedule of mlp_sh_kernel (see MlpProgram::sh_sched)
     for (int l = 0; l < 10; ++l) {
       const MlpLayer& L = P.layers[l];
-      const bool narrow = (L.n_half == 1);              // N = 128: two K blocks share a stage
-      const bool prev_acts = (l > 0);                   // the previous layer's epilogue wrote activation blocks
+      const int n_st = (int(L.n_kb) + 1) / 2;
       uint32_t seen = 0;
       int n = 0;
-      for (int kb = 0; kb < int(L.n_kb); kb += 2) {
-        // two K blocks per step (one ring stage for an N = 128 layer, two consecutive stages for N = 256): every named-
-        // barrier hand-off and commit of the issuer then carries 8 MMAs
-        const bool two = kb + 1 < int(L.n_kb) && L.a_blk[kb] != 0 && L.a_blk[kb + 1] != 0;
-        uint32_t need = 1u;                             // bit 0: accumulator drained by the slot's previous epilogue
-        for (int j = 0; j < (two ? 2 : 1); ++j) {
-          const int b = L.a_blk[kb + j];
-          if (b >= 1 && prev_acts) need |= 2u << ((b - 1) >> 1);   // bit 1 / 2: columns 0-127 / 128-255 of the previous layer written
+      for (int h = 0; h < int(L.n_half); ++h)
+        for (int s = 0; s < n_st; ++s) {
+          uint32_t need = 1u << h;   // accumulator half h drained by the previous layer's epilogue
+          for (int j = 0; j < 2; ++j) {
+            const int kb = 2 * s + j;
+            if (kb < int(L.n_kb) && int(L.a_blk[kb]) >= 1) need |= 1u << ((int(L.a_blk[kb]) - 1) >> 1);   // hid_blk0 = 1
+          }
+          need &= ~seen;
+          seen |= need;
+          const bool two = 2 * s + 1 < int(L.n_kb);
+          uint32_t w = uint32_t(L.a_blk[2 * s] & 15) | (uint32_t(two ? (L.a_blk[2 * s + 1] & 15) : 0) << 4) | (two ? 1u << 8 : 0u) | (need << 9);
+          if (s == n_st - 1) w |= 1u << 12;
+          if (L.lo_h != 0xFF && int(L.lo_h) == h && int(L.lo_s) == s) w |= 1u << 13;
+          w |= uint32_t(h) << 14;
+          if (s == 0) w |= 1u << 15;
+          if (!two && L.a_blk[2 * s] == 0) {   // the step's only K block is the tile input: it travels through the ring
+            w |= 1u << 16;
+            if (h == 0) w |= 1u << 17;                        // fetched here (one ring stage per slot, right after the weight stage)
+            if (h == int(L.n_half) - 1) w |= 1u << 18;        // ... and released here
+            if (L.flags & LF_WAIT_IN) w |= 1u << 19;          // view block: 27 features -> two K steps
+          }
+          w |= uint32_t(s) << 20;
+          P.sh_sched[l][n++] = w;
         }
-        need &= ~seen;
-        seen |= need;
-        uint32_t w = uint32_t(L.a_blk[kb] & 15) | (uint32_t(two ? (L.a_blk[kb + 1] & 15) : 0) << 4) | (two ? 1u << 8 : 0u) | (need << 9);
-        if (kb + 2 >= int(L.n_kb)) w |= 1u << 12;
-        if (narrow) w |= 1u << 14;
-        if (kb == 0) w |= 1u << 15;
-        if (!two && L.a_blk[kb] == 0) {   // the step's K block is the tile input: it travels through the ring, right after the weights
-          w |= 1u << 16;
-          if (L.flags & LF_WAIT_IN) w |= 1u << 19;   // view block: 27 features -> two K steps
-        }
-        w |= uint32_t(n) << 20;
-        P.sh_sched[l][n++] = w;
-      }
       P.sh_steps[l] = uint8_t(n);
     }
     P.alpha_w_off = kShAlphaW;
@@ -708,16 +719,8 @@ adn_status check_device_error(adn_ctx* ctx) {
   int err = 0;
   cudaError_t e = cudaDeviceSynchronize();
   err = *reinterpret_cast<volatile int*>(ctx->h_err);
-  if (e != cudaSuccess && !err) {
-    std::string ck;   // debug builds (ADN_SH_CKPT) leave per-role progress markers behind the flag
-    for (int i = 1; i < 12; ++i) ck += " " + std::to_string(ctx->h_err[i]);
-    return fail(ctx, ADN_ERR_CUDA, std::string("device synchronize: ") + cudaGetErrorString(e) + " [ckpt" + ck + "]");
-  }
-  if (err) {
-    std::string ck;
-    for (int i = 1; i < 12; ++i) ck += " " + std::to_string(ctx->h_err[i]);
-    return fail(ctx, ADN_ERR_KERNEL, "device watchdog: mbarrier wait timed out at site " + std::to_string(err & 0xfff) + " [ckpt" + ck + "]");
-  }
+  if (e != cudaSuccess && !err) return cuda_fail(ctx, e, "device synchronize");
+  if (err) return fail(ctx, ADN_ERR_KERNEL, "device watchdog: mbarrier wait timed out at site " + std::to_string(err & 0xfff));
   return ADN_OK;
 }
 
@@ -785,8 +788,8 @@ adn_status adn_create(adn_ctx** out, const adn_scene* scene, int device) {
             cudaMemcpy(ctx->d_zlut, lut, sizeof(lut), cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMalloc(&ctx->d_total, sizeof(long long)) == cudaSuccess &&
             cudaMemset(ctx->d_total, 0, sizeof(long long)) == cudaSuccess &&
-            cudaHostAlloc(&ctx->h_err, 64 * sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
-            cudaHostGetDevicePointer(&ctx->d_err, ctx->h_err, 0) == cudaSuccess && (std::memset(ctx->h_err, 0, 64 * sizeof(int)), true) &&
+            cudaHostAlloc(&ctx->h_err, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer(&ctx->d_err, ctx->h_err, 0) == cudaSuccess && (*ctx->h_err = 0, true) &&
             cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   if (!ok) {

@@ -65,13 +65,14 @@ struct MlpProgram {
   uint32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;  // float offsets in `side`
   int32_t out_cols;           // row stride of the FINAL_RAW output
   MlpLayer layers[kMaxLayers];
-  // mlp_sh_kernel: the issue schedule of one slot's pass over a layer, one word per step (= one ring stage of weights),
-  // precomputed on the host so that the MMA issuers decode instead of deriving it (their instruction count per step is
-  // on the kernel's critical path).  Bits: 0-3 / 4-7 activation block of the step's first / second K block (0 = tile
-  // input); 8 two K blocks (N = 128 layers); 9-11 what the slot needs here for the first time in this layer (9: its
-  // accumulator drained by the previous epilogue, 10 / 11: columns 0-127 / 128-255 of the previous layer written);
-  // 12 last step (commit acc_full); 14 N = 128; 15 first step (overwrite the accumulator); 16 the K block is the tile input
-  // (positions / view block), fetched into the ring stage after the weights; 19 view block (two K steps); 20-22 step index.
+  // mlp_sh_kernel: the issue schedule, one word per (layer, N half, stage) step in issue order, precomputed on the host so
+  // that the MMA issuer and the dependency helper decode instead of deriving it (the issuer's instruction count per
+  // 8-MMA group is the kernel's clock).  Bits: 0-3 / 4-7 activation block of K block 2s / 2s+1; 8 stage holds two K
+  // blocks; 9-10 dependencies a slot picks up here for the first time in this layer (9: previous layer's half-0 epilogue,
+  // 10: half-1 epilogue); 12 commit acc_full after this step; 13 commit lo_free; 14 N half; 15 first step of the half
+  // (accumulator is overwritten, not accumulated); 16 the step's K block is the tile input (positions / view block), an
+  // A operand that travels through the weight ring; 17 it is fetched at this step (two ring stages, one per slot, after
+  // the weight stage); 18 released after this step; 19 it is the view block (two K steps); 20-21 stage index in the half.
   uint32_t sh_sched[kMaxLayers][6];
   uint8_t sh_steps[kMaxLayers];
   // Biases and the two tiny heads live in the kernel parameter (constant) bank: every lane of a warp reads

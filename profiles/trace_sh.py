@@ -1,7 +1,6 @@
-"""Debug helper: timeline of mlp_sh_kernel on CTA 0 (adn_set_option "trace", 1): per (layer, slot) issue / accumulator ready /
-epilogue done, the issuers' wait per step, the producer's wait per stage, and the real SM clock of the launch (clock64
-against globaltimer).
-    python profiles/trace_sh.py"""
+"""Debug helper: per-(layer, half) timeline of mlp_sh_kernel on CTA 0 (adn_set_option "trace", 1): issue / accumulator
+ready / epilogue done, plus the real SM clock of the launch (clock64 against globaltimer).
+    python profiles/trace_sh.py [workload: rand|shaped]"""
 import ctypes as C
 import collections
 import os
@@ -10,11 +9,11 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adanerf_b200 import Renderer
 from adanerf_b200 import synthetic
 
+kind = sys.argv[1] if len(sys.argv) > 1 else "rand"
 scene = synthetic.SCENE_BARBERSHOP
 sd0, sd1 = synthetic.make_weights("rand", seed=0)
 r = Renderer(scene, device=0, sampling_net=sd0, shading_net=sd1)
@@ -28,65 +27,104 @@ torch.cuda.synchronize()
 buf = np.zeros(131072, dtype=np.int64)
 r.lib.adn_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
 assert r.lib.adn_debug_read_trace(r.handle, buf.ctypes.data, 131072) == 0
-os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-np.save(os.path.join(ROOT, "gpurun_out", "trace_sh_raw.npy"), buf)
+np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'trace_sh_raw.npy'), buf)
 c0, g0, c1, g1 = (int(x) for x in buf[7 * 8192:7 * 8192 + 4])
 if g1 > g0:
     print(f"kernel (CTA 0): {c1 - c0} SM cycles in {(g1 - g0) / 1e3:.1f} us -> SM clock {(c1 - c0) / (g1 - g0) * 1e3:.0f} MHz")
-
-
-def region(ri):
-    base = buf[ri * 8192:(ri + 1) * 8192]
-    n = int(base[0])
-    e = base[2:2 + 2 * n].reshape(-1, 2)
-    return [(int(t), ri, (int(c) >> 16) & 255, (int(c) >> 8) & 255, int(c) & 255) for t, c in e]
-
-
 rows = []
-for ri in range(5):
-    rows += region(ri)
+for region in range(3):
+    base = buf[region * 8192:(region + 1) * 8192]
+    n = int(base[0])
+    ev = base[2:2 + 2 * n].reshape(-1, 2)
+    rows += [(int(t), region, (int(c) >> 16) & 255, (int(c) >> 8) & 255, int(c) & 255) for t, c in ev]
 if not rows:
     raise SystemExit("no trace events (is the shading net on mlp_sh_kernel?)")
 t0 = min(x[0] for x in rows)
 rows = sorted((x[0] - t0,) + x[1:] for x in rows)
-names = {0: "step: wait", 6: "step: go", 1: "layer: first step go", 2: "layer: last step issued", 3: "acc seen", 4: "epi done"}
-who = {0: "issuer0", 1: "epi w0 slot0", 2: "epi w15 slot0", 3: "epi w0 slot1", 4: "epi w15 slot1"}
+names = {0: "step: before weight sync", 5: "step: weights ok", 6: "slot go", 1: "slot go (first step of half)", 2: "mma half issued", 3: "acc seen", 4: "epi done"}
 print("events", len(rows))
-starts = [i for i, x in enumerate(rows) if x[1] == 0 and x[3] == 0 and x[4] == 1]
+# one tile pair in the middle of the trace
+starts = [i for i, x in enumerate(rows) if x[1] == 0 and x[2] == 0 and x[3] == 0 and x[4] == 1]
 if len(starts) > 6:
     a, b = starts[5], starts[6]
-    print(f"tile-pair period (issuer 0, layer 0 -> next): {rows[b][0] - rows[a][0]} cycles")
+    print(f"tile-pair period (issuer, slot 0 layer 0 -> next): {rows[b][0] - rows[a][0]} cycles")
     for x in rows[a:b]:
-        if x[4] in (0, 6):
-            continue
-        print(f"{x[0] - rows[a][0]:8d}  {who[x[1]]:14s} layer={x[3]}  {names[x[4]]}")
+        print(f"{x[0] - rows[a][0]:8d}  {'mma ' if x[1] == 0 else 'epi%d' % x[1]} slot={x[2]} layer={x[3] >> 1} half={x[3] & 1}  {names[x[4]]}")
     per = [rows[starts[i + 1]][0] - rows[starts[i]][0] for i in range(2, len(starts) - 1)]
     print(f"tile-pair period: median {int(np.median(per))} min {min(per)} max {max(per)} (n={len(per)}); ideal tensor time 37376")
+# statistics
 last = {}
 per = collections.defaultdict(list)
-for t, reg, g, l, e in rows:
-    if reg == 0 and e in (1, 6) and (0, "w") in last:
-        per[("issuer 0: wait per step", -1)].append(t - last[(0, "w")])
-    if reg == 0 and e == 0:
-        last[(0, "w")] = t
-    if reg == 0 and e == 1:
-        last[(0, l, 1)] = t
-    if reg == 0 and e == 2 and (0, l, 1) in last:
-        per[("issuer 0: layer issue time", l)].append(t - last[(0, l, 1)])
-        last[(0, l, 2)] = t
-    if reg in (1, 3) and e == 3:
-        last[(reg, l, 3)] = t
-        if reg == 1 and (0, l, 2) in last:
-            per[("slot 0: last step issued -> acc seen", l)].append(t - last[(0, l, 2)])
-    if reg in (1, 3) and e == 4 and (reg, l, 3) in last:
-        per[("epilogue event (warp 0), slot %d" % (0 if reg == 1 else 1), l)].append(t - last[(reg, l, 3)])
+for t, reg, g, lh, e in rows:
+    last[(reg, g, lh, e)] = t
+    if reg == 0 and e == 1 and (0, g, lh, 0) in last:
+        per[("mma wait (sync)", lh)].append(t - last[(0, g, lh, 0)])
+    if reg == 0 and e == 2 and (0, g, lh, 1) in last:
+        per[("issue half", lh)].append(t - last[(0, g, lh, 1)])
+    if reg in (1, 2) and e == 3 and (0, g, lh, 2) in last:
+        per[("issued -> acc seen", lh)].append(t - last[(0, g, lh, 2)])
+    if reg in (1, 2) and e == 4 and (reg, g, lh, 3) in last:
+        per[("epilogue event slot %d" % g, lh)].append(t - last[(reg, g, lh, 3)])
 for k in sorted(per):
     v = np.array(per[k][8:])
     if len(v):
-        lab = "" if k[1] < 0 else f" layer {k[1]}"
-        print(f"{k[0]:40s}{lab}: median {int(np.median(v)):6d}  p90 {int(np.percentile(v, 90)):6d}  n={len(v)}")
+        print(f"{k[0]:26s} layer {k[1] >> 1} half {k[1] & 1}: median {int(np.median(v)):6d}  p90 {int(np.percentile(v, 90)):6d}  n={len(v)}")
+
+# producer (region 5) and helper (region 8)
+def region(ri):
+    base = buf[ri * 8192:(ri + 1) * 8192]
+    n = int(base[0])
+    e = base[2:2 + 2 * n].reshape(-1, 2)
+    return [(int(t) - t0, (int(c) >> 16) & 255, (int(c) >> 8) & 255, int(c) & 255) for t, c in e]
 pr = region(5)
-w = [b[0] - a[0] for a, b in zip(pr[0::2], pr[1::2]) if a[4] == 8 and b[4] == 9]
+w = [b[0] - a[0] for a, b in zip(pr[0::2], pr[1::2]) if a[3] == 8 and b[3] == 9]
 if w:
     w = np.array(w[16:])
     print(f"producer: wait for an empty stage median {int(np.median(w))} p90 {int(np.percentile(w, 90))} (n={len(w)})")
+hp = region(8)
+d = collections.defaultdict(list)
+cur = {}
+for t, g, lh, e in hp:
+    if e == 10:
+        cur[g] = t
+    elif e == 11 and g in cur:
+        d[g].append(t - cur[g])
+for g in sorted(d):
+    v = np.array(d[g][16:])
+    print(f"dependency helper, slot {g}: wait per sync point median {int(np.median(v))} p90 {int(np.percentile(v, 90))} mean {v.mean():.0f} (n={len(v)})")
+
+# issuer: per step, time spent at the weight barrier and at the dependency barriers
+iss = [x for x in rows if x[1] == 0]
+wsync, dsync = [], collections.defaultdict(list)
+prev = None
+for t, reg, g, lh, e in iss:
+    if e == 5 and prev and prev[4] == 0:
+        wsync.append(t - prev[0])
+    if e in (1, 6) and prev and prev[4] in (5, 1, 6, 2):
+        dsync[(g, e)].append(t - prev[0])
+    prev = (t, reg, g, lh, e)
+ws = collections.defaultdict(list)
+prev = None
+for t, reg, g, lh, e in iss:
+    if e in (1, 6) and prev and prev[4] == 0:
+        ws[e].append(t - prev[0])
+    prev = (t, reg, g, lh, e)
+for e in sorted(ws):
+    v = np.array(ws[e][16:])
+    print(f"issuer 0, wait for all barriers of a step ({'first step of a half' if e == 1 else 'later step'}): median {int(np.median(v))} p90 {int(np.percentile(v, 90))} mean {v.mean():.0f} (n={len(v)})")
+st = [b[0] - a[0] for a, b in zip([x for x in iss if x[4] == 0][:-1], [x for x in iss if x[4] == 0][1:])]
+if st:
+    v = np.array(st[16:])
+    print(f"issuer 0, step period: median {int(np.median(v))} p90 {int(np.percentile(v, 90))} mean {v.mean():.0f}; 1024 tensor cycles per full step")
+if wsync:
+    v = np.array(wsync[16:])
+    print(f"issuer at the weight barrier: median {int(np.median(v))} p90 {int(np.percentile(v, 90))} mean {v.mean():.0f}")
+for k in sorted(dsync):
+    v = np.array(dsync[k][16:])
+    print(f"issuer before slot {k[0]} go ({'first step of half' if k[1] == 1 else 'later step'}): median {int(np.median(v))} p90 {int(np.percentile(v, 90))} mean {v.mean():.0f}")
+hw = region(9); hp2 = region(10)
+if hw and hp2:
+    a = {(x[1], i): x[0] for i, x in enumerate(hw)}
+    d = [p[0] - l[0] for l, p in zip(hw, hp2)]
+    v = np.array(d[16:])
+    print(f"weight helper: peer's share seen after the local one by median {int(np.median(v))} p90 {int(np.percentile(v, 90))} cycles")
