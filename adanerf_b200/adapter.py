@@ -36,9 +36,10 @@ class B200Inference:
         # plots.render_all_imgs / the depth export read NeRFWeightsOutput, NeRFAlphaOutput, NeRFOutputDepth (src/plots.py:272-306)
         self.want_aux = bool(want_aux)
 
-    @classmethod
-    def from_train_config(cls, train_config, device=0):
-        """Builds the renderer from an initialised reference TrainConfig (models, feature sets, dataset_info)."""
+    @staticmethod
+    def args_from_train_config(train_config):
+        """(scene, [sampling_net, shading_net], threshold, K) read from an initialised reference TrainConfig -- no device
+        needed (tests/test_adapter_config.py runs this against the live reference)."""
         f1 = train_config.f_in[1]
         info = train_config.dataset_info
         scene = dict(view_cell_center=list(info.view.view_cell_center), view_cell_size=list(info.view.view_cell_size),
@@ -46,7 +47,13 @@ class B200Inference:
                      z_near=f1.z_near, z_far=f1.z_far)
         if getattr(f1, "useNDC", False):    # configs/*_ndc.ini: ndc_rays(self.h, self.w, self.view.focal, 1., ...) (features.py:430)
             scene.update(use_ndc=True, w=int(f1.w), h=int(f1.h), focal=float(info.view.focal))
-        return cls(scene, train_config.models[0], train_config.models[1], f1.z_sampler.threshold, f1.n_ray_samples, device=device)
+        return scene, [train_config.models[0], train_config.models[1]], float(f1.z_sampler.threshold), int(f1.n_ray_samples)
+
+    @classmethod
+    def from_train_config(cls, train_config, device=0):
+        """Builds the renderer from an initialised reference TrainConfig (models, feature sets, dataset_info)."""
+        scene, models, thr, k = cls.args_from_train_config(train_config)
+        return cls(scene, models[0], models[1], thr, k, device=device)
 
     def inference(self, batch_idx, gradient=False, **kwargs):
         if gradient:

@@ -23,11 +23,17 @@ SHADING_KEYS = ("pts_linears.0.weight", "views_linears.0.weight", "feature_linea
                 "rgb_linear.weight")
 
 
-def load_weights_file(path):
-    """state_dict (name -> fp32 CPU tensor) of a `.weights` file, whichever of the two forms it holds."""
+def load_weights_file(path, allow_pickle=False):
+    """state_dict (name -> fp32 CPU tensor) of a `.weights` file.  The reference saves a plain state_dict
+    (src/models.py:87-90), which torch loads without executing pickled code; a file that holds a pickled nn.Module
+    (older checkpoints) is only read with `allow_pickle=True` -- unpickling runs arbitrary code from the file, so that is
+    the caller's explicit decision (--allow-pickle on the command line), never a silent fallback."""
     try:
         obj = torch.load(path, map_location="cpu", weights_only=True)
-    except Exception:   # a pickled nn.Module (older checkpoints): needs the defining classes importable
+    except Exception as e:
+        if not allow_pickle:
+            raise ValueError(f"{path}: not a plain state_dict ({type(e).__name__}); pass allow_pickle=True / --allow-pickle "
+                             "to unpickle it (only for files you trust)") from e
         obj = torch.load(path, map_location="cpu", weights_only=False)
     if not isinstance(obj, (dict, OrderedDict)):
         obj = obj.state_dict()
@@ -61,8 +67,8 @@ def read_dataset_info(path):
     return {k: vals[k] for k in need}
 
 
-def weights_to_export_dir(weights0, weights1, out_dir, scene, threshold, num_samples):
-    sd0, sd1 = load_weights_file(weights0), load_weights_file(weights1)
+def weights_to_export_dir(weights0, weights1, out_dir, scene, threshold, num_samples, allow_pickle=False):
+    sd0, sd1 = load_weights_file(weights0, allow_pickle), load_weights_file(weights1, allow_pickle)
     check_state_dicts(sd0, sd1)
     write_export_dir(out_dir, scene, sd0, sd1, float(threshold), int(num_samples))
     return sd0, sd1
@@ -76,8 +82,10 @@ def main(argv=None):
     ap.add_argument("--threshold", type=float, required=True, help="adaptiveSamplingThreshold")
     ap.add_argument("--samples", type=int, required=True, help="numRaymarchSamples of the shading net (K)")
     ap.add_argument("--out", required=True)
+    ap.add_argument("--allow-pickle", action="store_true",
+                    help="also read checkpoints that hold a pickled nn.Module (executes code from the file: trusted files only)")
     a = ap.parse_args(argv)
-    weights_to_export_dir(a.weights0, a.weights1, a.out, read_dataset_info(a.dataset_info), a.threshold, a.samples)
+    weights_to_export_dir(a.weights0, a.weights1, a.out, read_dataset_info(a.dataset_info), a.threshold, a.samples, a.allow_pickle)
     print(f"wrote {a.out}")
 
 

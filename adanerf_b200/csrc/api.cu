@@ -68,9 +68,10 @@ struct adn_ctx {
   // pinned staging for the *_host entry points
   Stage2Sync s2sync;              // epoch / ticket base of s2scratch (no per-launch memset)
   Buf h_in, h_out, h_ns;
-  // caller buffers page-locked in place (cudaHostRegister) so repeated calls DMA straight from / to them
-  struct Reg { const void* p = nullptr; size_t bytes = 0; const void* last_seen = nullptr; };
-  Reg reg[3];
+  // caller buffers page-locked in place at the caller's explicit request (adn_register_host_buffer): the *_host entry
+  // points DMA straight from / to them; everything else goes through the context's pinned staging buffers
+  struct Reg { const void* p = nullptr; size_t bytes = 0; };
+  std::vector<Reg> regs;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev[8] = {};
   adn_stats stats{};
@@ -115,32 +116,18 @@ adn_status ensure_pinned(adn_ctx* ctx, Buf& b, size_t bytes) {
   return ADN_OK;
 }
 
-// Page-locks a caller buffer in place (slot: 0 = dirs in, 1 = rgb out, 2 = n_samples out).  Returns false when the
-// driver refuses (e.g. read-only or already-registered memory): the caller then goes through the staging buffer.
-bool pin_in_place(adn_ctx* ctx, int slot, const void* p, size_t bytes) {
-  adn_ctx::Reg& r = ctx->reg[slot];
-  if (r.p == p && r.bytes >= bytes) return true;
+// True when [p, p + bytes) can be the source / target of an asynchronous copy at full speed: inside a range the caller
+// registered with adn_register_host_buffer (whose lifetime the caller vouches for), or memory the caller allocated
+// page-locked itself (cudaMallocHost / torch pin_memory).  The library never registers memory behind the caller's back:
+// a buffer that is freed and re-allocated at the same address would keep a stale registration.
+bool pin_in_place(adn_ctx* ctx, int /*slot*/, const void* p, size_t bytes) {
+  const char* lo = static_cast<const char*>(p);
+  for (const adn_ctx::Reg& r : ctx->regs)
+    if (lo >= static_cast<const char*>(r.p) && lo + bytes <= static_cast<const char*>(r.p) + r.bytes) return true;
   cudaPointerAttributes attr{};
-  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;   // already pinned
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;
   cudaGetLastError();
-  // cudaHostRegister costs milliseconds: only pay it for a buffer the caller demonstrably reuses (same pointer on
-  // two consecutive calls); one-shot buffers go through the context's pinned staging area.
-  if (r.last_seen != p) {
-    r.last_seen = p;
-    return false;
-  }
-  if (r.p) {
-    cudaHostUnregister(const_cast<void*>(r.p));
-    r.p = nullptr;
-    r.bytes = 0;
-  }
-  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  r.p = p;
-  r.bytes = bytes;
-  return true;
+  return false;
 }
 
 // ---- bf16 helpers (host) -------------------------------------------------------------------
@@ -808,7 +795,7 @@ void adn_destroy(adn_ctx* ctx) {
                  &ctx->rayidx, &ctx->zbuf, &ctx->zpbuf, &ctx->tiles1, &ctx->raw1,  &ctx->s2scratch, &ctx->rgb,   &ctx->rgba, &ctx->x1, &ctx->metric, &ctx->enc_scratch};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
-  for (auto& r : ctx->reg)
+  for (auto& r : ctx->regs)
     if (r.p) cudaHostUnregister(const_cast<void*>(r.p));
   Buf* pinned[] = {&ctx->h_in, &ctx->h_out, &ctx->h_ns};
   for (Buf* b : pinned)
@@ -949,6 +936,53 @@ adn_status adn_render_camera_rgba8(adn_ctx* ctx, const float* pose, const float*
   const CameraRays cam = make_camera(ctx, W, H, row0);
   return render_impl(ctx, pose, rot, nullptr, &cam, int64_t(rows) * W, thr, K, nullptr, d_rgba8, nullptr, nullptr,
                      static_cast<cudaStream_t>(stream));
+}
+
+adn_status adn_render_camera_surface(adn_ctx* ctx, const float* pose, const float* rot, int W, int H, int row0, int rows,
+                                     float thr, int K, unsigned long long surface, void* stream) {
+  if (!ctx || W < 1 || H < 1 || row0 < 0 || rows < 0 || row0 + rows > H || !surface)
+    return fail(ctx, ADN_ERR_INVALID, "render_camera_surface: bad image window / surface");
+  ADN_CUDA(ctx, cudaSetDevice(ctx->device));
+  adn_status s = ensure(ctx, ctx->rgba, size_t(rows) * W * 4);
+  if (s != ADN_OK) return s;
+  uint8_t* px = static_cast<uint8_t*>(ctx->rgba.p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  s = adn_render_camera_rgba8(ctx, pose, rot, W, H, row0, rows, thr, K, px, stream);
+  if (s != ADN_OK) return s;
+  ADN_CUDA(ctx, launch_rgba_to_surface(px, W, row0, rows, surface, st));
+  ctx->stats.kernel_launches++;
+  return ADN_OK;
+}
+
+adn_status adn_register_host_buffer(adn_ctx* ctx, const void* p, size_t bytes) {
+  if (!ctx || !p || bytes == 0) return fail(ctx, ADN_ERR_INVALID, "register_host_buffer: bad arguments");
+  ADN_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (const adn_ctx::Reg& r : ctx->regs)
+    if (r.p == p) return fail(ctx, ADN_ERR_INVALID, "register_host_buffer: already registered (unregister first)");
+  ADN_CUDA(ctx, cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault));
+  ctx->regs.push_back({p, bytes});
+  return ADN_OK;
+}
+
+adn_status adn_unregister_host_buffer(adn_ctx* ctx, const void* p) {
+  if (!ctx || !p) return fail(ctx, ADN_ERR_INVALID, "unregister_host_buffer: bad arguments");
+  for (size_t i = 0; i < ctx->regs.size(); ++i)
+    if (ctx->regs[i].p == p) {
+      ADN_CUDA(ctx, cudaSetDevice(ctx->device));
+      ADN_CUDA(ctx, cudaDeviceSynchronize());   // no copy of an earlier call may still target the buffer
+      ADN_CUDA(ctx, cudaHostUnregister(const_cast<void*>(p)));
+      ctx->regs.erase(ctx->regs.begin() + long(i));
+      return ADN_OK;
+    }
+  return fail(ctx, ADN_ERR_INVALID, "unregister_host_buffer: not registered");
+}
+
+adn_status adn_net_dims(adn_ctx* ctx, int net_id, int* n_in, int* n_out) {
+  if (!ctx || (net_id != 0 && net_id != 1)) return fail(ctx, ADN_ERR_INVALID, "net_dims: bad arguments");
+  if (!ctx->net[net_id].ready) return fail(ctx, ADN_ERR_NO_WEIGHTS, "net_dims: network not set");
+  if (n_in) *n_in = ctx->net[net_id].n_in;
+  if (n_out) *n_out = ctx->net[net_id].n_out;
+  return ADN_OK;
 }
 
 adn_status adn_render_rays_host(adn_ctx* ctx, const float* pose, const float* rot, const float* h_dirs, int64_t n_rays,

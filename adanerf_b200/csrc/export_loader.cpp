@@ -49,14 +49,20 @@ bool next_field(Cursor& c, Field& f) {
   f.size = 0;
   switch (f.wire) {
     case 0: f.value = c.varint(); break;
-    case 1: f.data = c.p; f.size = 8; c.p += 8; break;
+    case 1:
+      if (size_t(c.end - c.p) < 8) { c.ok = false; return false; }   // truncated file: an error, not "end of message"
+      f.data = c.p; f.size = 8; c.p += 8;
+      break;
     case 2: {
       const uint64_t n = c.varint();
       if (!c.ok || n > uint64_t(c.end - c.p)) { c.ok = false; return false; }
       f.data = c.p; f.size = size_t(n); c.p += n;
       break;
     }
-    case 5: f.data = c.p; f.size = 4; c.p += 4; break;
+    case 5:
+      if (size_t(c.end - c.p) < 4) { c.ok = false; return false; }
+      f.data = c.p; f.size = 4; c.p += 4;
+      break;
     default: c.ok = false; return false;
   }
   return c.ok && c.p <= c.end;

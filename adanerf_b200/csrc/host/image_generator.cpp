@@ -54,6 +54,18 @@ bool ImageGenerator::inference(const Camera& camera, uint8_t* d_rgba8, int batch
   return s == ADN_OK;
 }
 
+bool ImageGenerator::inference(Camera& camera, unsigned long long output_surf, int batch_size, int num_samples,
+                               std::vector<::FeatureSet*>& /*feature_sets*/, std::vector<::Encoding>& /*encodings*/) {
+  if (!ctx_) return false;
+  float rot[9];
+  camera.rotation(rot);
+  if (batch_size > 0) adn_set_option(ctx_, "chunk_rays", batch_size);
+  const adn_status s = adn_render_camera_surface(ctx_, camera.pos, rot, camera.width, camera.height, 0, camera.height, thr_, num_samples,
+                                                 output_surf, nullptr);
+  if (s != ADN_OK) err_ = adn_last_error(ctx_);
+  return s == ADN_OK;
+}
+
 bool ImageGenerator::inference_host(const Camera& camera, float* h_rgb, int batch_size, int num_samples, int32_t* h_nsamples) {
   if (!ctx_) return false;
   float rot[9];

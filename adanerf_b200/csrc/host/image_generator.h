@@ -11,6 +11,13 @@
 
 #include "../../../include/adanerf_b200.h"
 
+// The viewer's own types that appear in ImageGenerator::inference's parameter list (include/featureset.h:25,
+// include/encoding.h:10).  The replacement never looks inside them -- the features and encodings of the hot path live in
+// the CUDA kernels behind the C ABI -- so forward declarations are all it needs; in the viewer build they resolve to the
+// viewer's classes and NeuralRenderer::render (neuralrenderer.cpp:158-160) compiles unchanged.
+class FeatureSet;
+class Encoding;
+
 namespace adn_host {
 
 // Counterpart of Config (config.cpp:270-344): what the export directory says.
@@ -44,6 +51,12 @@ class ImageGenerator {
   // ImageGenerator::inference (imagegenerator.cpp:247-478): renders the camera's frame.  `batch_size` is
   // the rays-per-batch knob of the viewer (-bs); `num_samples` = K.  d_rgba8: device buffer [W*H] uchar4.
   bool inference(const Camera& camera, uint8_t* d_rgba8, int batch_size, int num_samples, void* stream = nullptr);
+  // The reference's parameter list, verbatim (include/imagegenerator.h:61-62; called from neuralrenderer.cpp:158-160):
+  // `output_surf` is the cudaSurfaceObject_t of the GL-registered render buffer (buffermanager.h:34) and receives uchar4
+  // pixels through surf2Dwrite (adaptive_cuda_kernels.cu:846-851); the feature-set / encoding vectors are accepted and
+  // ignored.
+  bool inference(Camera& camera, unsigned long long /*cudaSurfaceObject_t*/ output_surf, int batch_size, int num_samples,
+                 std::vector<::FeatureSet*>& feature_sets, std::vector<::Encoding>& encodings);
   // Same into a host fp32 buffer [W*H*3] (copies inside).
   bool inference_host(const Camera& camera, float* h_rgb, int batch_size, int num_samples, int32_t* h_nsamples = nullptr);
 

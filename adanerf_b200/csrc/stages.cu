@@ -956,4 +956,18 @@ cudaError_t launch_image_sqdiff(const float* d_a, const float* d_b, long long n_
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------- viewer surface
+__global__ void rgba_to_surface_kernel(const uchar4* __restrict__ px, int W, int row0, int rows, cudaSurfaceObject_t surf) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < W && y < rows) surf2Dwrite(px[size_t(y) * W + x], surf, x * int(sizeof(uchar4)), row0 + y);
+}
+
+cudaError_t launch_rgba_to_surface(const uint8_t* d_rgba8, int W, int row0, int rows, unsigned long long surface, cudaStream_t s) {
+  if (rows <= 0 || W <= 0) return cudaSuccess;
+  const dim3 block(32, 8), grid(unsigned((W + 31) / 32), unsigned((rows + 7) / 8));
+  rgba_to_surface_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const uchar4*>(d_rgba8), W, row0, rows, cudaSurfaceObject_t(surface));
+  return cudaGetLastError();
+}
+
 }  // namespace adn

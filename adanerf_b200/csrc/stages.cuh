@@ -76,6 +76,9 @@ cudaError_t launch_stage5(const float* d_raw1, const float* d_zp, const float* d
                           const int32_t* d_offset, const int32_t* d_count, long long n_rays, int K, int dense,
                           float* d_rgb, uint8_t* d_rgba8, const Stage5Aux& aux, cudaStream_t s);
 
+// Linear RGBA8 pixels [rows * W] -> surf2Dwrite(uchar4, surface, 4 x, row0 + y) (adaptive_cuda_kernels.cu:846-851).
+cudaError_t launch_rgba_to_surface(const uint8_t* d_rgba8, int W, int row0, int rows, unsigned long long surface, cudaStream_t s);
+
 // Image metric (src/evaluate.py:49-54): sum over all values of (a - b)^2 in double, deterministic two-stage
 // reduction.  d_partials: kMetricBlocks doubles of scratch; d_sum receives the total.  clamp01: clip `a` to [0,1] first
 // (what the reference does to an image before it is written / compared as 8-bit, src/evaluate.py:257-258).

@@ -16,6 +16,8 @@ def _varint(buf, pos):
     result = 0
     shift = 0
     while True:
+        if pos >= len(buf) or shift > 63:
+            raise ValueError("truncated or corrupt protobuf varint")
         b = buf[pos]
         pos += 1
         result |= (b & 0x7F) << shift
@@ -34,13 +36,19 @@ def _fields(buf, start, end):
             v, pos = _varint(buf, pos)
             yield fn, wt, v
         elif wt == 1:
+            if pos + 8 > end:
+                raise ValueError("truncated protobuf message")
             yield fn, wt, (pos, pos + 8)
             pos += 8
         elif wt == 2:
             ln, pos = _varint(buf, pos)
+            if pos + ln > end:
+                raise ValueError("truncated protobuf message")
             yield fn, wt, (pos, pos + ln)
             pos += ln
         elif wt == 5:
+            if pos + 4 > end:
+                raise ValueError("truncated protobuf message")
             yield fn, wt, (pos, pos + 4)
             pos += 4
         else:

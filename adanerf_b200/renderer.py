@@ -46,6 +46,7 @@ class Renderer:
         self.lib = _lib.load_library()
         self.device = int(device)
         self.handle = C.c_void_p()
+        self._registered = {}    # address -> numpy array page-locked through register_host_buffer (kept alive here)
         self.n_feat0 = 90        # sampling-net input features (30 with the "2-2" encoding of the NDC configs)
         if _handle is not None:
             self.handle = _handle
@@ -80,8 +81,9 @@ class Renderer:
 
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.adn_destroy(self.handle)
+            self.lib.adn_destroy(self.handle)      # also ends every host-buffer registration
             self.handle = None
+            self._registered = {}
 
     def __del__(self):
         try:
@@ -104,6 +106,23 @@ class Renderer:
 
     def set_option(self, name, value):
         self._check(self.lib.adn_set_option(self.handle, name.encode(), int(value)))
+
+    def net_dims(self, net_id):
+        n_in, n_out = C.c_int(), C.c_int()
+        self._check(self.lib.adn_net_dims(self.handle, int(net_id), C.byref(n_in), C.byref(n_out)))
+        return n_in.value, n_out.value
+
+    def register_host_buffer(self, array):
+        """Page-locks a numpy array in place so render_rays_host / render_camera_host DMA straight from / to it.  The
+        renderer keeps a reference (the memory must outlive the registration); unregister_host_buffer or close() ends it."""
+        if not (isinstance(array, np.ndarray) and array.flags["C_CONTIGUOUS"]):
+            raise ValueError("register_host_buffer: need a C-contiguous numpy array")
+        self._check(self.lib.adn_register_host_buffer(self.handle, array.ctypes.data, array.nbytes))
+        self._registered[array.ctypes.data] = array
+
+    def unregister_host_buffer(self, array):
+        self._check(self.lib.adn_unregister_host_buffer(self.handle, array.ctypes.data))
+        self._registered.pop(array.ctypes.data, None)
 
     def stats(self):
         s = Stats()
@@ -184,8 +203,9 @@ class Renderer:
         return out
 
     def render_rays_host(self, pose, rot, dirs_np, thr, K, want_nsamples=True, out=None):
-        """Host buffers in, host buffers out (H2D / D2H inside the call).  Reusing `dirs_np` / `out` across calls lets
-        the library page-lock them in place and DMA without a staging copy."""
+        """Host buffers in, host buffers out (H2D / D2H inside the call).  Arrays registered with register_host_buffer
+        (or already page-locked) are DMA'd in place; anything else -- including the temporaries a dtype / layout
+        conversion creates here -- goes through the context's pinned staging buffers."""
         p, r = self._pose_rot(pose, rot)
         d = np.ascontiguousarray(dirs_np, dtype=np.float32).reshape(-1, 3)
         n = d.shape[0]
@@ -234,9 +254,12 @@ class Renderer:
                                                  ro.data_ptr(), rd.data_ptr(), self._stream()))
         return x0, ro, rd
 
-    def mlp0(self, x0, n_out=128):
+    def mlp0(self, x0, n_out=None):
         x = self._f32(x0)
-        out = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=self._dev())
+        width = self.net_dims(0)[1]              # the library writes [N, n_out of the network that is set]
+        if n_out is not None and int(n_out) != width:
+            raise ValueError(f"mlp0: the sampling net has {width} outputs, not {n_out}")
+        out = torch.empty((x.shape[0], width), dtype=torch.float32, device=self._dev())
         self._check(self.lib.adn_mlp0_forward(self.handle, x.data_ptr(), x.shape[0], out.data_ptr(), self._stream()))
         return out
 
@@ -291,15 +314,35 @@ class Renderer:
 _RENDERERS = {}
 
 
+def _fingerprint(net):
+    """Changes whenever a parameter tensor is replaced or modified in place (torch bumps `_version` on in-place writes)."""
+    sd = net.state_dict() if hasattr(net, "state_dict") else net
+    return tuple((k, v.data_ptr(), v._version, tuple(v.shape)) if isinstance(v, torch.Tensor) else (k, id(v)) for k, v in sd.items())
+
+
 def render(rays, sampling_net, shading_net, adaptiveSamplingThreshold, *, K, scene, device=0):
     """The public entry named by BASELINE.json.  `rays` = dict(pose [3], rot [3,3], dirs [N,3]) -- the
     three tensors `TrainConfig.inference` reads from its batch (ImagePose, ImageRotation,
-    RayDirectionsSamples; src/features.py:832-834).  Returns (rgb [N,3], n_samples [N])."""
-    key = (id(sampling_net), id(shading_net), device, tuple(sorted((k, str(v)) for k, v in scene.items())))
-    r = _RENDERERS.get(key)
-    if r is None:
-        r = Renderer(scene, device=device, sampling_net=sampling_net, shading_net=shading_net)
+    RayDirectionsSamples; src/features.py:832-834).  Returns (rgb [N,3], n_samples [N]).
+
+    Like the reference's inference() it always renders with the CURRENT parameters: the packed device copy of the two
+    networks is cached, but the cache entry holds the networks themselves (their ids cannot be recycled) and is
+    re-packed whenever a parameter tensor was replaced or written in place since the last call."""
+    key = (device, tuple(sorted((k, str(v)) for k, v in scene.items())))
+    entry = _RENDERERS.get(key)
+    fp = (_fingerprint(sampling_net), _fingerprint(shading_net))
+    if entry is None or entry["nets"][0] is not sampling_net or entry["nets"][1] is not shading_net:
+        if entry is not None:
+            entry["renderer"].close()
         _RENDERERS.clear()
-        _RENDERERS[key] = r
-    out = r.render_rays(rays["pose"], rays["rot"], rays["dirs"], adaptiveSamplingThreshold, K)
+        entry = dict(renderer=Renderer(scene, device=device, sampling_net=sampling_net, shading_net=shading_net),
+                     nets=(sampling_net, shading_net), fp=fp)
+        _RENDERERS[key] = entry
+    elif entry["fp"] != fp:
+        if entry["fp"][0] != fp[0]:
+            entry["renderer"].set_weights(0, sampling_net)
+        if entry["fp"][1] != fp[1]:
+            entry["renderer"].set_weights(1, shading_net)
+        entry["fp"] = fp
+    out = entry["renderer"].render_rays(rays["pose"], rays["rot"], rays["dirs"], adaptiveSamplingThreshold, K)
     return out["rgb"], out["n_samples"]

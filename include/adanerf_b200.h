@@ -17,6 +17,7 @@
 #ifndef ADANERF_B200_H
 #define ADANERF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -153,12 +154,32 @@ adn_status adn_render_camera(adn_ctx* ctx, const float* pose, const float* rot, 
 adn_status adn_render_camera_rgba8(adn_ctx* ctx, const float* pose, const float* rot, int W, int H, int row0, int rows,
                                    float thr, int K, uint8_t* d_rgba8, void* stream);
 
+/* The viewer's own output target: a cudaSurfaceObject_t bound to the GL-registered cudaArray of the current render buffer
+ * (adanerf_real_time_viewer/src/interoprenderbuffer.cpp:53-83); uchar4 pixels written with surf2Dwrite at (x, row0 + y)
+ * exactly like adaptive_cuda_kernels.cu:846-851.  `surface` is the cudaSurfaceObject_t value (an unsigned 64-bit handle;
+ * the header stays free of CUDA types). */
+adn_status adn_render_camera_surface(adn_ctx* ctx, const float* pose, const float* rot, int W, int H, int row0, int rows,
+                                     float thr, int K, unsigned long long surface, void* stream);
+
 /* End-to-end variants with HOST buffers: H2D of the inputs and D2H of the results happen inside the
- * call (pinned staging owned by the context) and the call returns after the results are on the host. */
+ * call and the call returns after the results are on the host.  Buffers the caller registered (below) or allocated
+ * page-locked itself are the source / target of the DMA; anything else goes through pinned staging owned by the
+ * context (one extra host copy each way). */
 adn_status adn_render_rays_host(adn_ctx* ctx, const float* pose, const float* rot, const float* h_dirs, int64_t n_rays,
                                 float thr, int K, float* h_rgb, int32_t* h_nsamples);
 adn_status adn_render_camera_host(adn_ctx* ctx, const float* pose, const float* rot, int W, int H, int row0, int rows,
                                   float thr, int K, float* h_rgb, int32_t* h_nsamples);
+
+/* Page-locks [p, p + bytes) in place (cudaHostRegister) for the *_host entry points.  The caller owns the memory and must
+ * keep it allocated until adn_unregister_host_buffer / adn_destroy: the library never registers memory on its own (a
+ * buffer freed and re-allocated at the same address would keep a stale registration).  The viewer's equivalent is the
+ * GL-registered cudaArray of InteropRenderbuffer (adanerf_real_time_viewer/src/interoprenderbuffer.cpp:53-83). */
+adn_status adn_register_host_buffer(adn_ctx* ctx, const void* p, size_t bytes);
+adn_status adn_unregister_host_buffer(adn_ctx* ctx, const void* p);
+
+/* Input / output width of a network set with adn_set_weights (sampling net: n_out is 128 in a render, the stage-level
+ * adn_mlp0_forward also accepts test networks with 256 outputs and writes [N, n_out]). */
+adn_status adn_net_dims(adn_ctx* ctx, int net_id, int* n_in, int* n_out);
 
 /* ---- stage-level entry points (parity tests drive each kernel in isolation) ------------- */
 /* stage 0: SpherePosDir.batch (src/features.py:845-899). d_x0 [N,90] fp32 (dir block first), d_ray_o/d [N,3]. */

@@ -26,6 +26,19 @@ def test_library_exports_every_header_symbol(lib):
         assert hasattr(lib, s), s
 
 
+def test_multi_library_exports_every_header_symbol():
+    """libadanerf_b200_multi.so (one process, G devices, NCCL gather): header == exports == ctypes shim."""
+    import __graft_entry__ as g
+    g.build()
+    hdr = open(os.path.join(ROOT, "include", "adanerf_b200_multi.h")).read()
+    declared = set(re.findall(r"\b(adn_multi_[a-z0-9_]+)\s*\(", hdr))
+    from adanerf_b200.multi import SYMBOLS
+    assert declared == set(SYMBOLS), (declared ^ set(SYMBOLS))
+    mlib = ctypes.CDLL(g.MULTI_LIB)
+    for s in declared:
+        assert hasattr(mlib, s), s
+
+
 def test_sass_is_blackwell_native():
     """tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, bulk async copy -> UBLKCP (B200_PROFILING.md)."""
     import shutil

@@ -31,7 +31,7 @@ def test_inference_adapter_matches_reference(case):
     outs, dicts = inf.inference(batch, gradient=False, is_inference=True)
     rgb = outs[-1][:, :3].cpu().numpy()
     np.testing.assert_array_equal(dicts[-1]["AdaptiveSamplePositions"].cpu().numpy(), g["asp"])
-    assert orc.psnr(rgb, g["rgb"]) > 45.0
+    assert orc.psnr(rgb, g["rgb"]) >= 49.4
     assert torch.equal(dicts[-1]["PostProcessedNetworkOutput"], outs[-1])
     with pytest.raises(NotImplementedError):
         inf.inference(batch, gradient=True)
@@ -69,3 +69,35 @@ def test_inference_adapter_auxiliary_dict_entries():
     same = np.round(d1["AdaptiveSamplePositions"].cpu().numpy() * K) == np.round(g["asp"] * K)
     np.testing.assert_allclose(d1["NeRFOutputDepth"].cpu().numpy()[same], g["depth_est"][same], rtol=0, atol=2e-2)
     np.testing.assert_allclose(d1["NeRFWeightsOutput"].cpu().numpy()[same], g["weights"][same], rtol=0, atol=2e-2)
+
+
+class _NS:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _duck_train_config(m, sd0, sd1, K, thr):
+    """An object with exactly the attributes B200Inference.from_train_config reads from an initialised reference
+    TrainConfig (tests/test_adapter_config.py pins those names against the live reference on a CPU box)."""
+    sp = m["scene_params"]
+    view = _NS(view_cell_center=sp["view_cell_center"], view_cell_size=sp["view_cell_size"], fov=sp["fov"], focal=None)
+    f1 = _NS(depth_range=sp["depth_range"], max_depth=sp["max_depth"], z_near=0.001, z_far=1.0, useNDC=False,
+             z_sampler=_NS(threshold=thr), n_ray_samples=K)
+    return _NS(f_in=[None, f1], dataset_info=_NS(view=view), models=[sd0, sd1])
+
+
+def test_from_train_config_renders_like_the_reference():
+    """The line INTEGRATION.md tells a maintainer to paste: B200Inference.from_train_config(train_config)."""
+    from adanerf_b200.adapter import B200Inference
+    from oracle import adanerf_oracle as orc
+    g = load_golden("pav_k8_t0.2")
+    m = g["meta"]
+    sd0, sd1 = case_weights("pav_k8_t0.2")
+    inf = B200Inference.from_train_config(_duck_train_config(m, sd0, sd1, m["K"], m["thr"]))
+    assert inf.K == m["K"] and abs(inf.threshold - m["thr"]) < 1e-7
+    batch = _Batch({"ImagePose": torch.from_numpy(g["pose"]).reshape(1, 3).cuda(),
+                    "ImageRotation": torch.from_numpy(g["rot"]).reshape(1, 3, 3).cuda(),
+                    "RayDirectionsSamples": torch.from_numpy(g["dirs"]).reshape(1, -1, 3).cuda()})
+    outs, dicts = inf.inference(batch, gradient=False, is_inference=True)
+    np.testing.assert_array_equal(dicts[-1]["AdaptiveSamplePositions"].cpu().numpy(), g["asp"])
+    assert orc.psnr(outs[-1][:, :3].cpu().numpy(), g["rgb"]) >= 49.4

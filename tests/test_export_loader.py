@@ -143,3 +143,37 @@ def test_render_from_ndc_export_dir_matches_state_dict(tmp_path):
     assert torch.isfinite(a).all() and torch.equal(a, b)
     r1.close()
     r2.close()
+
+
+def test_truncated_onnx_is_an_error_not_a_short_model(lib, tmp_path):
+    """A model file cut in the middle of a field must fail loading (ADN_ERR_IO / ValueError), not parse as a model with
+    fewer initialisers (next_field advanced past the end on fixed-width fields)."""
+    scene = orc.SCENE_PAVILLON
+    sd0, sd1 = orc.make_weights("rand", seed=2)
+    d = tmp_path / "export"
+    ow.write_export_dir(str(d), scene, sd0, sd1, 0.2, 8)
+    whole = (d / "model1.onnx").read_bytes()
+    for cut in (len(whole) - 1, len(whole) - 3, len(whole) // 2, 37):
+        (d / "model1.onnx").write_bytes(whole[:cut])
+        assert lib.adn_probe_export_dir(str(d).encode(), None, None, None, None) == 5, cut   # ADN_ERR_IO
+        with pytest.raises(ValueError):
+            ow.read_onnx_initializers(str(d / "model1.onnx"))
+    # a fixed-width field (wire type 1 / 5) whose payload is missing
+    (d / "model1.onnx").write_bytes(whole + bytes([0x09, 0x01, 0x02]))      # field 1, wire type 1, 2 of 8 bytes
+    assert lib.adn_probe_export_dir(str(d).encode(), None, None, None, None) == 5
+    with pytest.raises(ValueError):
+        ow.read_onnx_initializers(str(d / "model1.onnx"))
+
+
+def test_pickled_module_checkpoints_need_an_explicit_flag(tmp_path):
+    """`.weights` files are plain state_dicts (src/models.py:87-90); anything that needs unpickling is refused unless
+    the caller opts in."""
+    from adanerf_b200 import convert
+    net = torch.nn.Linear(3, 2)
+    torch.save(net, tmp_path / "module.weights")            # a pickled nn.Module
+    with pytest.raises(ValueError, match="allow_pickle"):
+        convert.load_weights_file(tmp_path / "module.weights")
+    sd = convert.load_weights_file(tmp_path / "module.weights", allow_pickle=True)
+    assert set(sd) == {"weight", "bias"}
+    torch.save(net.state_dict(), tmp_path / "plain.weights")
+    assert set(convert.load_weights_file(tmp_path / "plain.weights")) == {"weight", "bias"}

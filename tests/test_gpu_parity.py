@@ -112,7 +112,7 @@ def test_mlp0_matches_reference(case):
     flips = ((raw0 >= g["meta"]["thr"]) != (g["raw0"] >= g["meta"]["thr"])).mean()
     print(f"{case}: |ours-ref|={err_ref:.2e} |ours-f64|={err64:.2e} |ref-f64|={noise:.2e} threshold flips={flips:.2e}")
     assert err64 < 5e-5, "split-precision sampling MLP must be fp32-class"
-    assert flips < 2e-4
+    assert flips <= 3.1e-5              # at most one borderline cell of the 256 x 128 (SURVEY.md 8d budget: flips <= 1e-5 .. 3e-5)
     r.close()
 
 
@@ -217,7 +217,7 @@ def test_mlp1_matches_reference(case):
     print(f"{case}: max|raw1 err|={err.max():.3e} (scale {scale:.2f}) PSNR(sigmoid)={p:.1f} dB")
     assert np.isfinite(raw1).all()
     assert err.max() < 0.05 * scale
-    assert p > 45.0
+    assert p >= 49.4
     r.close()
 
 
@@ -275,13 +275,13 @@ def test_render_matches_reference(case):
     p = orc.psnr(rgb, g["rgb"])
     print(f"{case}: rays with identical sample count {same.mean():.4f}; PSNR(ours, reference) = {p:.2f} dB")
     assert np.isfinite(rgb).all()
-    assert same.mean() >= 0.98
+    assert same.mean() >= 0.999         # contract: identical sample count on >= 99.9 % of the rays
     np.testing.assert_allclose(out["oracle_weights"].cpu().numpy(), g["raw0"], rtol=0, atol=2e-4 * max(1, np.abs(g["raw0"]).max()))
     if case.startswith("rand"):
         # untrained nets: alpha*zp leaves [0,1] and amplifies -> relative check only
         assert np.abs(rgb - g["rgb"]).max() < 0.05 * max(1.0, np.abs(g["rgb"]).max())
     else:
-        assert p > 45.0
+        assert p >= 49.4                # |dPSNR| < 0.05 dB for a 30 dB scene
     host = r.render_rays_host(g["pose"], g["rot"], g["dirs"], m["thr"], m["K"])
     np.testing.assert_array_equal(host["rgb"], rgb)          # host-buffer entry == device entry, bitwise
     np.testing.assert_array_equal(host["n_samples"], ns)
@@ -303,7 +303,7 @@ def test_render_auxiliary_outputs(case):
     assert torch.equal(out["rgb"], plain["rgb"])                     # asking for more does not change the image
     ns = out["n_samples"].cpu().numpy()
     same = (ns == np.round(g["asp"] * K).astype(np.int32))
-    assert same.mean() >= 0.98
+    assert same.mean() >= 0.999
     w, a, z = (out[k].cpu().numpy() for k in ("weights", "alpha", "z_vals"))
     # padding exactly like the reference's: zeros / NaN behind the ray's samples
     slot = np.arange(K)[None, :] >= ns[:, None]
@@ -400,7 +400,7 @@ def test_full_frame_properties_and_tiling():
     p = orc.psnr(full["rgb"].cpu()[idx], ref["rgb"])
     same = (full["n_samples"].cpu()[idx].long() == ref["n_samples"]).float().mean().item()
     print(f"full frame subset: PSNR {p:.2f} dB, identical counts {same:.4f}, mean spr {full['n_samples'].float().mean():.2f}")
-    assert p > 45.0 and same > 0.98
+    assert p >= 49.4 and same >= 0.999
     rgba = r.render_camera_rgba8(pose, rot, W, H, 0.2, 8, row0=0, rows=4).cpu()
     expect = (full["rgb"][:4 * W].clamp(0, 1) * 255.0).to(torch.uint8).cpu()
     assert torch.equal(rgba[:, :3], expect) and bool((rgba[:, 3] == 255).all())
@@ -559,7 +559,7 @@ def test_render_k32_uses_the_general_kernels():
         same = (out["n_samples"].cpu().long() == ref["n_samples"]).float().mean().item()
         p = orc.psnr(out["rgb"].cpu().numpy(), ref["rgb"].numpy())
         print(f"K={K} thr={thr}: mean spr {ref['n_samples'].float().mean():.2f}, identical counts {same:.4f}, PSNR {p:.2f} dB")
-        assert same >= 0.995 and p > 45.0
+        assert same >= 0.999 and p >= 49.4
     r.close()
 
 

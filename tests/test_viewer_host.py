@@ -49,3 +49,25 @@ def test_viewer_renders_export_dir(viewer, tmp_path):
     assert 1.0 <= float(m.group(2)) <= 8.0
     ppm = open(os.path.join(d, "adn_frame.ppm"), "rb").read()
     assert ppm.startswith(b"P6\n400 300\n255\n") and len(ppm) == len(b"P6\n400 300\n255\n") + 400 * 300 * 3
+
+
+@pytest.mark.gpu
+def test_viewer_frame_through_a_surface_object(viewer, tmp_path):
+    """ImageGenerator::inference(camera, cudaSurfaceObject_t, batch, K, feature_sets, encodings) -- the reference's
+    parameter list (adanerf_real_time_viewer/include/imagegenerator.h:61-62) -- writes the uchar4 frame into a
+    surface-bound cudaArray exactly like adaptive_cuda_kernels.cu:846-851; the program compares it with the fp32 frame."""
+    d = _export(tmp_path)
+    r = subprocess.run([viewer, d, "-s", "400", "300", "-f", "2", "--surface"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "surface frame 400x300: 0 mismatching bytes" in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_viewer_on_two_gpus_renders_the_same_frame(viewer, tmp_path):
+    """C++ host, one process, two devices, NCCL gather (include/adanerf_b200_multi.h): same checksum as the bands rendered on
+    one device."""
+    d = _export(tmp_path)
+    r2 = subprocess.run([viewer, d, "-s", "400", "301", "-f", "4", "-g", "2"], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    assert "on 2 GPUs" in r2.stdout and "checksum" in r2.stdout
