@@ -150,7 +150,7 @@ class Renderer:
     # ---- the hot path --------------------------------------------------------------------
     AUX_KEYS = ("weights", "alpha", "z_vals", "depth_map", "acc_map", "disp_map", "depth_est")
 
-    def render_rays(self, pose, rot, dirs, thr, K, want_nsamples=True, want_oracle_weights=False, want_aux=False):
+    def render_rays(self, pose, rot, dirs, thr, K, want_nsamples=True, want_oracle_weights=False, want_aux=False, out=None):
         """dirs [N,3] (cuda tensor) -> dict(rgb [N,3], n_samples [N] int32, oracle_weights [N,128]).
         want_aux: True or an iterable of AUX_KEYS -> additionally weights / alpha / z_vals [N,K] and depth_map /
         acc_map / disp_map / depth_est [N] (adaptive_raw2outputs' other outputs, src/nerf_raymarch_common.py:137-144;
@@ -158,7 +158,9 @@ class Renderer:
         p, r = self._pose_rot(pose, rot)
         d = self._f32(dirs).reshape(-1, 3)
         n = d.shape[0]
-        rgb = torch.empty((n, 3), dtype=torch.float32, device=self._dev())
+        if out is not None and (out.dtype != torch.float32 or out.numel() != 3 * n or not out.is_contiguous() or out.device != self._dev()):
+            raise ValueError("render_rays: out must be a contiguous float32 [N,3] tensor on the renderer's device")
+        rgb = out if out is not None else torch.empty((n, 3), dtype=torch.float32, device=self._dev())
         ns = torch.empty((n,), dtype=torch.int32, device=self._dev()) if want_nsamples else None
         ow = torch.empty((n, 128), dtype=torch.float32, device=self._dev()) if want_oracle_weights else None
         out = dict(rgb=rgb, n_samples=ns, oracle_weights=ow)

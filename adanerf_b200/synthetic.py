@@ -10,6 +10,22 @@ SCENE_BARBERSHOP = dict(
     depth_range=[-0.42766728550195693, 7.07244257926941], fov=1.5271797180175781,
     max_depth=8.704841423034669)
 
+# adanerf_real_time_viewer/sample_pavillon_16/dataset_info.txt (Pavillon; its trained networks ship with the reference)
+SCENE_PAVILLON = dict(
+    view_cell_center=[0.783, -3.19, 1.39], view_cell_size=[0.7, 0.7, 0.2],
+    depth_range=[0.1542200982570648, 8.358194804191589], fov=1.1386263370513916,
+    max_depth=8.79825210571289)
+
+
+def load_weights_npz(path):
+    """(sampling, shading) state_dicts from an .npz with keys `sd0/<name>`, `sd1/<name>` (tests/golden/weights_pavillon.npz:
+    the initialisers of sample_pavillon_16/model{0,1}.onnx, the reference's shipped trained networks)."""
+    import numpy as np
+    z = np.load(path, allow_pickle=False)
+    sd0 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0/")}
+    sd1 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd1/")}
+    return sd0, sd1
+
 
 def init_sampling_net(n_in=90, n_out=128, W=256, D=8):
     layers = [torch.nn.Linear(n_in, W)]
