@@ -256,7 +256,11 @@ adn_status build_net0(adn_ctx* ctx) {
       segs = {{0, 64}, {64, 64}, {128, 64}, {192, 64}};
     }
     L.n_kb = uint8_t(segs.size());
-    for (size_t i = 0; i < segs.size(); ++i) L.a_blk[i] = uint8_t(i);
+    for (size_t i = 0; i < segs.size(); ++i) {
+      L.a_blk[i] = uint8_t(i);
+      // 16-wide K steps that hold data; block 0 keeps at least one (it initialises the accumulator)
+      L.k_cnt[i] = uint8_t(std::max(i == 0 ? 1 : 0, (segs[i].valid + 15) / 16));
+    }
     L.n_half = uint8_t(n_out / 128);
     L.flags = last ? uint8_t(LF_FINAL_RAW) : uint8_t(LF_RELU | LF_OUT_ACT);
     L.out_blk0 = 0;

@@ -937,11 +937,14 @@ mlp_hp_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict
               const uint32_t b_lo = b_hi + (HALF >> 4);
               const uint32_t d = d_layer + uint32_t(nh * 128);
               if (elect_one()) {
+                const int nk = L.k_cnt[kb];   // zero-padded tail columns of an input block are not multiplied
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_hi + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
-                  umma_bf16_cg<CG>(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
-                  umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
+                  if (k < nk) {
+                    umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_hi + 2 * k), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16_cg<CG>(d, desc(a_lo + 2 * k), desc(b_hi + 2 * k), idesc128, 1u);
+                    umma_bf16_cg<CG>(d, desc(a_hi + 2 * k), desc(b_lo + 2 * k), idesc128, 1u);
+                  }
                 }
                 umma_commit_cg<CG>(&w_empty[stage]);
                 // the last MMAs of this layer that read hidden blocks 0,1 have been issued: half 0's epilogue may store

@@ -53,6 +53,9 @@ struct MlpLayer {
   // mlp_sh_kernel: the (N half, stage) of this layer after whose MMAs the blocks that half 0's epilogue overwrites in
   // place (out_blk0, out_blk0 + 1) are no longer read -- the issuer commits `lo_free` there.  0xFF: not used.
   uint8_t lo_h, lo_s;
+  // mlp_hp_kernel: 16-wide K steps issued per K block (4 = the whole 64-wide block; fewer when the tail columns of the
+  // block are zero padding, e.g. 90 input features -> blocks of 4 and 2 steps; 30 features -> 2 and 0).
+  uint8_t k_cnt[6];
 };
 
 struct MlpProgram {

@@ -495,7 +495,7 @@ def run_single_process(args, cfg, name):
     secs = time.perf_counter() - t0
     clocks = sampler.stop()
     render_ms, gather_ms = m.last_times()
-    host = np.empty((W * Hn, 3), np.float32)
+    host = torch.empty((W * Hn, 3), dtype=torch.float32).pin_memory().numpy()   # caller-owned page-locked frame buffer
     t0 = time.perf_counter()
     for _ in range(args.steps):
         m.render_camera(pose, rot, W, Hn, thr, K)

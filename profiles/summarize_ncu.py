@@ -15,7 +15,9 @@ want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_%"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_%"),
         ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp_insts"),
-        ("lts__t_bytes.sum", "l2_bytes"), ("launch__grid_size", "grid"), ("launch__block_size", "block")]
+        ("lts__t_bytes.sum", "l2_bytes"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_%"), ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+        ("sm__cycles_elapsed.max", "cycles")]
 
 
 def num(r, k):
@@ -30,7 +32,8 @@ def num(r, k):
     return x * scale
 
 
-out, md = {}, [f"# ncu --set full summary ({tag})\n", "| kernel | time ms | DRAM rd MB | DRAM wr MB | DRAM % | tensor % | issue % | warps % | regs | warp insts | L2 bytes MB | grid x block |",
+title = sys.argv[3] if len(sys.argv) > 3 else ""
+out, md = {}, [f"# ncu --set full --metrics lts__t_bytes.sum summary ({tag}) {title}\n", "| kernel | time ms | DRAM rd MB | DRAM wr MB | DRAM % | tensor % | issue % | warps % | regs | warp insts | L2 bytes MB | grid x block |",
                "|---|---|---|---|---|---|---|---|---|---|---|---|"]
 for r in rows[2:]:
     if len(r) != len(hdr):
