@@ -58,6 +58,7 @@ struct adn_ctx {
   int cta_group = 2;              // MLP kernels: 2 = CTA pairs (cta_group::2 MMAs), 1 = single CTA
   int64_t chunk_rays = 0;
   bool profile = false;
+  int weight_copies = 1;   // replicas of each packed weight blob (MlpProgram::w_copies)
   // scratch
   Buf tiles0, raw0, x0, ray_o, ray_d, dirs, count, offset, rayidx, zbuf, zpbuf, tiles1, raw1, s2scratch, rgb, rgba, x1, metric, enc_scratch;
   long long* d_total = nullptr;
@@ -214,8 +215,15 @@ adn_status upload(adn_ctx* ctx, Net& net, const std::vector<uint8_t>& wblob, con
   std::memcpy(net.prog.side, fblob.data(), fblob.size() * 4);
   if (net.d_wblob) cudaFree(net.d_wblob);
   net.d_wblob = nullptr;
-  ADN_CUDA(ctx, cudaMalloc(&net.d_wblob, wblob.size()));
-  ADN_CUDA(ctx, cudaMemcpy(net.d_wblob, wblob.data(), wblob.size(), cudaMemcpyHostToDevice));
+  // replicas of the blob (see MlpProgram::w_copies): stride = size rounded up to 4 KB plus an odd number of 256-byte units,
+  // so that the same offset of different copies lands in different L2 slices
+  const uint32_t copies = uint32_t(std::max(1, ctx->weight_copies));
+  const size_t stride = ((wblob.size() + 4095) / 4096) * 4096 + 256 * 37;
+  net.prog.w_copies = copies;
+  net.prog.w_stride = uint32_t(stride);
+  ADN_CUDA(ctx, cudaMalloc(&net.d_wblob, stride * copies));
+  for (uint32_t c = 0; c < copies; ++c)
+    ADN_CUDA(ctx, cudaMemcpy(net.d_wblob + stride * c, wblob.data(), wblob.size(), cudaMemcpyHostToDevice));
   return ADN_OK;
 }
 
@@ -747,6 +755,7 @@ adn_status adn_create(adn_ctx** out, const adn_scene* scene, int device) {
   ctx->num_sms = prop.multiProcessorCount;
   if (const char* cg = std::getenv("ADN_CTA_GROUP")) ctx->cta_group = (cg[0] == '1') ? 1 : 2;   // A/B experiments
   if (const char* sk = std::getenv("ADN_SHADING_KERNEL")) ctx->sh_kernel = (sk[0] != '0');
+  if (const char* wc = std::getenv("ADN_WEIGHT_COPIES")) ctx->weight_copies = std::max(1, std::min(64, std::atoi(wc)));
   ctx->scene = *scene;
   if (cudaSetDevice(device) != cudaSuccess) {
     delete ctx;

@@ -317,7 +317,7 @@ mlp_umma_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restri
           const uint32_t src_stride = (NSPLIT == 2 || L.n_half == 2) ? uint32_t(2 * kBlkBytes) : uint32_t(kBlkBytes);
           for (int g = 0; g < NG; ++g) {
             if (first_tile(iter, g) >= n_tiles) continue;
-            const uint8_t* src = wblob + L.w_off;
+            const uint8_t* src = wblob + size_t((blockIdx.x / CG) % prog.w_copies) * prog.w_stride + L.w_off;
             for (int i = 0; i < n_st; ++i) {
               if (l == 2) tr(5, g, stage, 8);
               mbar_wait(&w_empty[stage], phase ^ 1, err_flag, 1);
@@ -833,7 +833,7 @@ mlp_hp_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict
         for (int l = 0; l < n_layers; ++l) {
           const MlpLayer& L = prog.layers[l];
           const int n_st = int(L.n_kb) * int(L.n_half);
-          const uint8_t* src = wblob + L.w_off;
+          const uint8_t* src = wblob + size_t((blockIdx.x / CG) % prog.w_copies) * prog.w_stride + L.w_off;
           for (int i = 0; i < n_st; ++i) {
             mbar_wait(&w_empty[stage], phase ^ 1, err_flag, 1);
             uint8_t* dst = ring + size_t(stage) * STAGE_BYTES;

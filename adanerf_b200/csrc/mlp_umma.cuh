@@ -67,6 +67,10 @@ struct MlpProgram {
   uint32_t in0_off, in0_lo_off, in1_off;
   uint32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;  // float offsets in `side`
   int32_t out_cols;           // row stride of the FINAL_RAW output
+  // The packed weight blob is replicated w_copies times in global memory, w_stride bytes apart; CTA pair p streams copy
+  // p % w_copies.  Every CTA of a persistent launch re-reads the same ~1 MB every tile, nearly in lock step: with one copy
+  // the whole grid hammers the same few dozen L2 slices at a time and the fills queue up behind each other.
+  uint32_t w_copies, w_stride;
   MlpLayer layers[kMaxLayers];
   // mlp_sh_kernel: the issue schedule, one word per (layer, N half, stage) step in issue order, precomputed on the host so
   // that the MMA issuer and the dependency helper decode instead of deriving it (the issuer's instruction count per

@@ -255,6 +255,16 @@ __device__ __forceinline__ void umma_bf16_cg(uint32_t d_tmem, uint64_t a_desc, u
     umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
   }
 }
+// Same, A operand from tensor memory (each CTA's 128 rows x 16 bf16 = 8 columns of 32 bits at a_tmem): only B is read from
+// shared memory.
+__device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // commit: arrive on the mbarrier at this shared-memory offset in every CTA of the pair (mask 0b11)
 template <int CG>
 __device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
