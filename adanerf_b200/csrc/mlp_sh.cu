@@ -32,21 +32,27 @@
 //     and keep two TMEM loads in flight: the per-chunk latency chain (TMEM read, pack, store, proxy fence), not the
 //     instruction count, bounds the epilogue.
 //
-// What it buys and what bounds it now (profiles/trace_sh.py): 3-5 % over the round-1 kernel in
-// same-box A/B runs, half the L2 -> SM weight traffic, fp32-exact biases.  Not more, because SS-mode MMAs with 128 rows
-// per CTA read A (4 KB) and B (2 KB) from shared memory per N = 128 MMA: 96 B / clk at the nominal 64 cycles, against the
-// ~64 B / clk the tensor core gets from shared memory (exactly what N = 256 needs).  With an EMPTY epilogue the 580 MMAs
-// of a tile pair take 52.7 k cycles (91 per MMA, 71 % of the 64-cycle rate); the real epilogue's shared-memory traffic and
-// dependency latencies bring it to ~65 k.  Also measured and dropped (git history): a per-layer specialised epilogue with
-// immediate bias operands (160 KB of code: instruction-cache misses on every event, 2x slower); N = 256 MMAs with
-// alternating slots, per-slot weight passes, an early "accumulator drained" signal and half-wise activation hand-off
-// (5.3-5.7 ms: with a tensor queue only ~2 MMAs deep, the issuer's per-step barrier + commit overhead idles the pipe).
+// What it buys and what bounds it now (profiles/trace_sh.py): 3-12 % over the round-1 kernel in
+// same-box A/B runs (the power-capped boxes gain most), half the L2 -> SM weight traffic, fp32-exact biases; 60 % tensor pipe
+// active under ncu.  A tile pair (580 MMAs, 37.4 k tensor cycles at the 64-cycle rate) takes ~65 k cycles.  Timing probes
+// with deliberately incomplete kernels (ADN_SH_DIAG builds, wrong results, kept in git history) split the gap three ways:
+//     47.2 k  empty epilogue, no weight / input traffic at all: the two issuer warps alone.  A step is ~200 executed
+//             instructions (decode of the schedule word, ring bookkeeping, lane-parallel barrier wait, 8 MMAs at ~50 cycles
+//             each, commits); the tensor queue is ~2 MMAs deep, so the pipe idles whenever both issuers are between steps;
+//     53.0 k  + the weight ring: every step still waits ~0.3 k cycles for its stage although the copy was issued ~4.5 k cycles
+//             earlier (5 stages of 16 KB cannot cover the fill latency when two are borrowed by tile inputs);
+//     59.0 k  real epilogue, no weight traffic;      65 k  everything.
+// Ruled out by probes: the shared-memory A operand (A read from TMEM instead: 53.7 k against 53.0 k, no change -- the 91
+// cycles per N = 128 MMA are not an operand-bandwidth limit); L2 hot-spotting on the weight lines (1 / 4 / 16 / 37 replicas
+// of the blob, MlpProgram::w_copies: 4.89-4.96 ms, no change).  Measured and dropped (git history): an issue loop
+// specialised per schedule word (compile-time stages, 65 KB of code: 5.87 ms against 4.88 -- the footprint costs more
+// instruction-cache misses than the decode saved); a per-layer specialised epilogue with immediate bias operands (160 KB:
+// 2x slower, same reason); N = 256 MMAs with alternating slots, per-slot weight passes, an early "accumulator drained"
+// signal and half-wise activation hand-off (5.3-5.7 ms).
 //
 // Roles (19 warps): 16 epilogue warps, weight producer, 2 MMA issuers (leader CTA) / barrier forwarders (peer CTA).
 // Schedule walked by every role:
 //   for tile group:  for layer:  for half h:  for stage s (K blocks 2s, 2s+1):  for slot g:  8 MMAs (M 256, N 128, K 16)
-#include <type_traits>
-
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -57,9 +63,6 @@ namespace adn {
 
 namespace {
 
-#ifndef ADN_SH_TRACE2
-#define ADN_SH_TRACE2 0   // 1: extra issuer trace points (after the barrier wait, after the probe, after the MMA issue)
-#endif
 #ifndef ADN_SH_DIAG
 // Timing experiments only (wrong results): 1 = epilogue events do nothing, 2 = epilogue without shared-memory stores.
 #define ADN_SH_DIAG 0
@@ -69,13 +72,6 @@ constexpr int kShStages = 5;               // ring stages per CTA (a weight stag
 constexpr int kShStageBytes = kBlkBytes;   // weights: two K blocks x this CTA's 64 rows of the 128-row N half; or one input block
 constexpr int kShHalfBlk = kBlkBytes / 2;  // one K block of weights, this CTA's 64 B rows
 constexpr int kShNB = 4;                   // hidden activation blocks per slot
-
-// Issue schedule of the NeRF(8 x 256, skip 4, view branch) program, one word per step (bit layout: MlpProgram::sh_sched);
-// build_net1 derives the same words from the layer table and launch_mlp_sh refuses a program that differs.
-constexpr uint32_t kShSchedL0[2] = {0x3b200u, 0x5d400u};                                            // positions -> 256
-constexpr uint32_t kShSchedHid[4] = {0x8321u, 0x101543u, 0xe121u, 0x105143u};                       // 256 -> 256 (layers 1-4, 6-8)
-constexpr uint32_t kShSchedL5[6] = {0x8321u, 0x100543u, 0x231000u, 0xe121u, 0x104143u, 0x255000u};  // cat[h, positions] -> 256
-constexpr uint32_t kShSchedL9[3] = {0x8321u, 0x100543u, 0x2f1000u};                                 // cat[feature, view] -> 128
 
 enum : int { SK_RELU = 0, SK_RELU_ALPHA = 1, SK_LINEAR = 2, SK_RGB = 3 };
 
@@ -153,7 +149,7 @@ __device__ __forceinline__ void sh_chunk(const uint32_t (&r)[32], uint32_t side_
 template <int KIND>
 __device__ __forceinline__ void sh_event(uint32_t side_s, int boff, int c, uint32_t taddr, uint32_t st_row, uint32_t rx, bool wait_lo,
                                          uint64_t* lo_bar, uint32_t lo_parity, int* err_flag, float& alpha, float (&rgb)[3]) {
-  if (ADN_SH_DIAG == 1 || ADN_SH_DIAG == 5 || ADN_SH_DIAG == 6) {
+  if (ADN_SH_DIAG == 1) {
     if (KIND != SK_RGB && wait_lo) mbar_wait(lo_bar, lo_parity, err_flag, 6);
     return;
   }
@@ -260,9 +256,7 @@ mlp_sh_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict
     trace[7 * 8192 + 1] = gt;
   }
 
-  if (warp == kProducerWarp && (ADN_SH_DIAG == 6 || ADN_SH_DIAG == 7)) {
-    // timing probe: no weight / input traffic at all, the issuers never wait for a ring stage
-  } else if (warp == kProducerWarp) {
+  if (warp == kProducerWarp) {
     // ===================================================================== producer (weights and tile inputs)
     // Weight stage of step (l, h, s): K blocks 2s, 2s+1 of N half h, this CTA's rows [64 rank, +64) of each [128 x 64]
     // tile.  A step flagged "fetch input" is followed by one stage per slot holding that slot's tile input block.
@@ -339,133 +333,95 @@ mlp_sh_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict
         phase ^= 1;
       }
     };
-    // The issue schedule of the NeRF program is a compile-time constant (kShSched*, checked against MlpProgram::sh_sched by
-    // the launcher): every step below is specialised on its schedule word, so the issuing warp executes ~50 instructions per
-    // 8-MMA step instead of the ~200 a decoded word costs (measured: with nothing to wait for, the decoding loop alone kept
-    // the tensor pipe at 79 %).
-    bool active = false;
-    auto step = [&](auto wc, int l, int i) {
-      constexpr uint32_t w = decltype(wc)::value;
-      constexpr uint32_t need_c = (w >> 9) & 3u;
-      constexpr bool fetch = (w & (1u << 17)) != 0;
-      constexpr bool input = (w & (1u << 16)) != 0;
-      constexpr uint32_t h = (w >> 14) & 1u;
-      const uint32_t need = (active && leader) ? need_c : 0u;
-      const int w_stage = stage;
-      const uint32_t w_par = phase;
-      advance();
-      uint32_t in_par = 0;
-      if constexpr (fetch) {   // input stages: slot 0's, then slot 1's
-        if (g == 1) {
-          in_other = stage;
-          advance();
-        }
-        in_stage = stage;
-        in_par = phase;
-        advance();
-        if (g == 0) {
-          in_other = stage;
-          advance();
-        }
-      }
-      if (lane == 0 && g == 0) tr(0, i, 2 * l + int(h), 0);
-      {
-        // one barrier per lane: 0, 1: previous layer's half-0 / half-1 epilogue of this slot (both CTAs arrive on the
-        // leader's barrier); 2: this slot's input stage; 3: the weight stage (in the leader: own share + the peer's forward).
-        // Everybody waits for the weight stage: a warp that ran ahead by a full ring phase would alias the parity of a later
-        // phase.
-        const bool probe = (ADN_SH_DIAG == 6 || ADN_SH_DIAG == 7);
-        const bool mine = lane < 2 ? (need_c != 0 && ((need >> lane) & 1u) != 0) : (probe ? false : (lane == 2 ? fetch : (lane == 3 && !w_seen)));
-        uint64_t* bar = lane < 2 ? &act_ready[2 * g + (lane & 1)] : (lane == 2 ? &w_full[in_stage] : &w_full[w_stage]);
-        const uint32_t parity = lane < 2 ? ((ar_phase >> (lane & 1)) & 1u) : (lane == 2 ? in_par : w_par);
-        mbar_wait_lanes(bar, parity, mine, err_flag, 3);
-        if (!probe && !leader && ((lane == 2 && fetch) || (lane == 3 && g == 0))) mbar_arrive_remote(mapa_shared(smem_u32(bar), 0));
-        __syncwarp();
-        ar_phase ^= need;
-      }
-#if ADN_SH_TRACE2
-      if (lane == 0 && g == 0) tr(0, i, 2 * l + int(h), 7);
-#endif
-      // Early, non-blocking probe of the NEXT step's weight stage (ring position `stage` after the advances above): its
-      // round trip overlaps the MMA issue below instead of draining the tensor pipe's short queue at the next step.
-      w_seen = (ADN_SH_DIAG == 6 || ADN_SH_DIAG == 7) ? false : ((lane == 3) ? mbar_test(&w_full[stage], phase) : false);
-#if ADN_SH_TRACE2
-      if (lane == 0 && g == 0) tr(0, i, 2 * l + int(h), 8);
-#endif
-      if (leader) {
-        tc_fence_after();
-        if (lane == 0 && g == 0) tr(0, g, 2 * l + int(h), (w & (1u << 15)) ? 1 : 6);
-        constexpr uint32_t acc = ((w >> 15) & 1u) ^ 1u;   // first step of the half: overwrite
-        const uint32_t b = ring_lo + uint32_t(w_stage) * (STAGE_BYTES >> 4);
-        const uint32_t a0 = input ? ring_lo + uint32_t(in_stage) * (STAGE_BYTES >> 4) : act_lo0 + ((w & 15u) - 1u) * (kBlkBytes >> 4);
-        const uint32_t a1 = act_lo0 + (((w >> 4) & 15u) - 1u) * (kBlkBytes >> 4);
-        const uint32_t d = tmem_base + uint32_t(g * 256) + h * 128u;
-        if (elect_one()) {
-          if (active) {
-            if (ADN_SH_DIAG == 5 && !input) {
-              // timing probe: hidden-layer A operand from tensor memory (the other slot's accumulator columns: garbage)
-              const uint32_t at = tmem_base + uint32_t((g ^ 1) * 256);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_ts_cg2(d, at + 8u * k, desc(b + 2 * k), idesc128, k == 0 ? acc : 1u);
-              if constexpr ((w & (1u << 8)) != 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_ts_cg2(d, at + 32u + 8u * k, desc(b + (HALF >> 4) + 2 * k), idesc128, 1u);
-              }
-            } else {
-              umma_bf16_cg<2>(d, desc(a0), desc(b), idesc128, acc);
-              umma_bf16_cg<2>(d, desc(a0 + 2), desc(b + 2), idesc128, 1u);
-              if constexpr (!(w & (1u << 19))) {   // the view block carries 27 features: two K steps
-                umma_bf16_cg<2>(d, desc(a0 + 4), desc(b + 4), idesc128, 1u);
-                umma_bf16_cg<2>(d, desc(a0 + 6), desc(b + 6), idesc128, 1u);
-              }
-              if constexpr ((w & (1u << 8)) != 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_cg<2>(d, desc(a1 + 2 * k), desc(b + (HALF >> 4) + 2 * k), idesc128, 1u);
-              }
-            }
-            if constexpr ((w & (1u << 12)) != 0) umma_commit_cg<2>(&acc_full[2 * g + int(h)]);
-            if constexpr ((w & (1u << 13)) != 0) umma_commit_cg<2>(&lo_free[g]);
-          }
-          umma_commit_cg<2>(&w_empty[w_stage]);
-          if constexpr ((w & (1u << 18)) != 0) {   // the tile-input stages of both slots are released here (every stage expects two commits)
-            umma_commit_cg<2>(&w_empty[in_stage]);
-            umma_commit_cg<2>(&w_empty[in_other]);
-          }
-        }
-        __syncwarp();
-#if ADN_SH_TRACE2
-        if (lane == 0 && g == 0) tr(0, i, 2 * l + int(h), 9);
-#endif
-        if constexpr ((w & (1u << 12)) != 0) {
-          if (lane == 0 && g == 0) tr(0, g, 2 * l + int(h), 2);
-        }
-      }
-    };
-#define ADN_SHW(x) std::integral_constant<uint32_t, (x)> {}
-    auto hidden_layer = [&](int l) {   // 256 -> 256: two K blocks per step, two steps per N half
-      step(ADN_SHW(kShSchedHid[0]), l, 0);
-      step(ADN_SHW(kShSchedHid[1]), l, 1);
-      step(ADN_SHW(kShSchedHid[2]), l, 2);
-      step(ADN_SHW(kShSchedHid[3]), l, 3);
-    };
     for (long long iter = 0;; ++iter) {
       if (first_tile(iter, 0) >= n_tiles) break;
-      active = first_tile(iter, g) < n_tiles;
-      step(ADN_SHW(kShSchedL0[0]), 0, 0);
-      step(ADN_SHW(kShSchedL0[1]), 0, 1);
-      for (int l = 1; l <= 4; ++l) hidden_layer(l);
-      step(ADN_SHW(kShSchedL5[0]), 5, 0);
-      step(ADN_SHW(kShSchedL5[1]), 5, 1);
-      step(ADN_SHW(kShSchedL5[2]), 5, 2);
-      step(ADN_SHW(kShSchedL5[3]), 5, 3);
-      step(ADN_SHW(kShSchedL5[4]), 5, 4);
-      step(ADN_SHW(kShSchedL5[5]), 5, 5);
-      for (int l = 6; l <= 8; ++l) hidden_layer(l);
-      step(ADN_SHW(kShSchedL9[0]), 9, 0);
-      step(ADN_SHW(kShSchedL9[1]), 9, 1);
-      step(ADN_SHW(kShSchedL9[2]), 9, 2);
+      const bool active = first_tile(iter, g) < n_tiles;
+      for (int l = 0; l < n_layers; ++l) {
+        const int n_steps = prog.sh_steps[l];
+        uint32_t seen = 0;
+        for (int i = 0; i < n_steps; ++i) {
+          const uint32_t w = prog.sh_sched[l][i];
+          const uint32_t need = (active && leader) ? ((w >> 9) & 3u) : 0u;
+          seen |= need;
+          const int w_stage = stage;
+          const uint32_t w_par = phase;
+          advance();
+          uint32_t in_par = 0;
+          const bool fetch = (w & (1u << 17)) != 0;
+          if (fetch) {   // input stages: slot 0's, then slot 1's
+            if (g == 1) {
+              in_other = stage;
+              advance();
+            }
+            in_stage = stage;
+            in_par = phase;
+            advance();
+            if (g == 0) {
+              in_other = stage;
+              advance();
+            }
+          }
+          if (lane == 0 && g == 0) tr(0, i, 2 * l + int((w >> 14) & 1u), 0);
+          {
+            // one barrier per lane: 0, 1: previous layer's half-0 / half-1 epilogue of this slot (both CTAs arrive on the
+            // leader's barrier); 2: this slot's input stage; 3: the weight stage (in the leader: own share + the peer's forward)
+            const bool mine = lane < 2 ? ((need >> lane) & 1u) != 0 : (lane == 2 ? fetch : (lane == 3 && !w_seen));   // everybody waits for the weight
+            // stage: a warp that ran ahead by a full ring phase would alias the parity of a later phase
+            uint64_t* bar = lane < 2 ? &act_ready[2 * g + (lane & 1)] : (lane == 2 ? &w_full[in_stage] : &w_full[w_stage]);
+            const uint32_t parity = lane < 2 ? ((ar_phase >> (lane & 1)) & 1u) : (lane == 2 ? in_par : w_par);
+            mbar_wait_lanes(bar, parity, mine, err_flag, 3);
+            if (!leader && ((lane == 2 && fetch) || (lane == 3 && g == 0))) mbar_arrive_remote(mapa_shared(smem_u32(bar), 0));
+            __syncwarp();
+            ar_phase ^= need;
+          }
+          // Early, non-blocking probe of the NEXT step's weight stage (ring position `stage` after the advances above): its
+          // round trip overlaps the MMA issue below instead of draining the tensor pipe's short queue at the next step.
+          w_seen = (lane == 3) ? mbar_test(&w_full[stage], phase) : false;
+          if (leader) {
+            tc_fence_after();
+            if (lane == 0 && g == 0) tr(0, g, 2 * l + int((w >> 14) & 1u), (w & (1u << 15)) ? 1 : 6);
+            const uint32_t h = (w >> 14) & 1u;
+            const uint32_t acc = ((w >> 15) & 1u) ^ 1u;   // first step of the half: overwrite
+            const uint32_t b = ring_lo + uint32_t(w_stage) * (STAGE_BYTES >> 4);
+            const bool input = (w & (1u << 16)) != 0;
+            const uint32_t a0 = input ? ring_lo + uint32_t(in_stage) * (STAGE_BYTES >> 4) : act_lo0 + ((w & 15u) - 1u) * (kBlkBytes >> 4);
+            const uint32_t a1 = act_lo0 + (((w >> 4) & 15u) - 1u) * (kBlkBytes >> 4);
+            const uint32_t d = tmem_base + uint32_t(g * 256) + h * 128u;
+            if (elect_one()) {
+              if (active) {
+                umma_bf16_cg<2>(d, desc(a0), desc(b), idesc128, acc);
+                umma_bf16_cg<2>(d, desc(a0 + 2), desc(b + 2), idesc128, 1u);
+                if (!(w & (1u << 19))) {   // the view block carries 27 features: two K steps
+                  umma_bf16_cg<2>(d, desc(a0 + 4), desc(b + 4), idesc128, 1u);
+                  umma_bf16_cg<2>(d, desc(a0 + 6), desc(b + 6), idesc128, 1u);
+                }
+                if (w & (1u << 8)) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_bf16_cg<2>(d, desc(a1 + 2 * k), desc(b + (HALF >> 4) + 2 * k), idesc128, 1u);
+                }
+                if (w & (1u << 12)) umma_commit_cg<2>(&acc_full[2 * g + int(h)]);
+                if (w & (1u << 13)) umma_commit_cg<2>(&lo_free[g]);
+              }
+              umma_commit_cg<2>(&w_empty[w_stage]);
+              if (w & (1u << 18)) {   // the tile-input stages of both slots are released here (every stage expects two commits)
+                umma_commit_cg<2>(&w_empty[in_stage]);
+                umma_commit_cg<2>(&w_empty[in_other]);
+              }
+            }
+            __syncwarp();
+            if (lane == 0 && g == 0 && (w & (1u << 12))) tr(0, g, 2 * l + int(h), 2);
+          }
+        }
+        // one completion per layer and (slot, half): consume what this layer did not need (leader only; not reached by the
+        // NeRF program, every layer of which needs both halves)
+        const uint32_t rest = (active && leader) ? (3u & ~seen) : 0u;
+        if (rest) {
+          mbar_wait_lanes(&act_ready[2 * g + (lane & 1)], (ar_phase >> (lane & 1)) & 1u, lane < 2 && ((rest >> lane) & 1u) != 0, err_flag, 9);
+          __syncwarp();
+          ar_phase ^= rest;
+        }
+      }
     }
-#undef ADN_SHW
   } else {
     // ============================================================================ epilogue (2 x 8 warps)
     // Warps 0..7 serve slot 0, warps 8..15 slot 1; events in the issuer's completion order: for layer, for half.  Every warp
@@ -593,17 +549,6 @@ cudaError_t set_max_dyn_smem_once(const void* func, int bytes, unsigned long lon
 cudaError_t launch_mlp_sh(const MlpProgram& prog, const uint8_t* wblob, const uint8_t* in_tiles, float* out, const long long* rows_dev,
                           long long rows_host, int* err_flag, int num_sms, cudaStream_t stream, long long* trace) {
   static unsigned long long attr_done = 0;
-  {   // the kernel's issue loop is specialised on this schedule
-    auto same = [&](int l, const uint32_t* ref, int n) {
-      if (int(prog.sh_steps[l]) != n) return false;
-      for (int i = 0; i < n; ++i)
-        if (prog.sh_sched[l][i] != ref[i]) return false;
-      return true;
-    };
-    bool ok = prog.n_layers == kShLayers && same(0, kShSchedL0, 2) && same(5, kShSchedL5, 6) && same(9, kShSchedL9, 3);
-    for (int l : {1, 2, 3, 4, 6, 7, 8}) ok = ok && same(l, kShSchedHid, 4);
-    if (!ok) return cudaErrorInvalidValue;
-  }
   const size_t smem = size_t(2) * kShNB * kBlkBytes + size_t(kShStages) * kShStageBytes + size_t(kSideFloats) * 4 + 512 /*barriers*/ +
                       1024 /*alignment slack*/;
   cudaError_t e = set_max_dyn_smem_once(reinterpret_cast<const void*>(mlp_sh_kernel), int(smem), &attr_done);
