@@ -605,7 +605,7 @@ adn_status render_chunk(adn_ctx* ctx, const PoseDev& pd, const float* d_dirs, co
 
   if (timing) cudaEventRecord(ctx->ev[0], st);
   // stage 0
-  if (n0.nsplit == 2 && n0.n_in == 90) {
+  if (n0.nsplit == 2 && (n0.n_in == 90 || n0.n_in == 30) && n0.n_in == ctx->n_feat0) {   // stage 0 writes the packed hi / lo tiles itself
     ADN_CUDA(ctx, launch_stage0(ctx->sc, pd, d_dirs, cam, n, nullptr, ray_o, ray_d, tiles0, st));
     ctx->stats.kernel_launches++;
   } else {

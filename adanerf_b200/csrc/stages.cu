@@ -152,10 +152,13 @@ cudaError_t launch_stage0(const SceneDev& sc, const PoseDev& pd, const float* d_
       set_max_dyn_smem_once(reinterpret_cast<const void*>(stage0_kernel<false>), 4 * kBlkBytes, &attr_rays) != cudaSuccess)
     return cudaGetLastError();
   if (cam) c = *cam;
-  if (sc.n_freq_pos0 == 2 && sc.n_freq_dir0 == 2) {   // "2-2": fp32 rows only (the generic pack kernel builds the tiles)
-    if (d_tiles0) return cudaErrorInvalidValue;
-    if (cam) stage0_kernel<true, 2, 2><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, nullptr);
-    else stage0_kernel<false, 2, 2><<<grid, 128, 0, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, nullptr);
+  if (sc.n_freq_pos0 == 2 && sc.n_freq_dir0 == 2) {   // "2-2" (NDC configs): 30 features, same tile image (columns 30.. are zero)
+    static unsigned long long attr_cam22 = 0, attr_rays22 = 0;
+    if (set_max_dyn_smem_once(reinterpret_cast<const void*>(stage0_kernel<true, 2, 2>), 4 * kBlkBytes, &attr_cam22) != cudaSuccess ||
+        set_max_dyn_smem_once(reinterpret_cast<const void*>(stage0_kernel<false, 2, 2>), 4 * kBlkBytes, &attr_rays22) != cudaSuccess)
+      return cudaGetLastError();
+    if (cam) stage0_kernel<true, 2, 2><<<grid, 128, smem, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
+    else stage0_kernel<false, 2, 2><<<grid, 128, smem, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
   } else if (cam) {
     stage0_kernel<true><<<grid, 128, smem, s>>>(sc, pd, d_dirs, c, n_rays, d_x0, d_ray_o, d_ray_d, d_tiles0);
   } else {

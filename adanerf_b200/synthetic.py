@@ -17,6 +17,10 @@ SCENE_PAVILLON = dict(
     max_depth=8.79825210571289)
 
 
+# the NDC / LLFF variant (configs/fine_training_ndc.ini) on the same geometry: the dataset's w, h feed ndc_rays (features.py:430)
+SCENE_PAVILLON_NDC = dict(SCENE_PAVILLON, use_ndc=True, w=800, h=800)
+
+
 def load_weights_npz(path):
     """(sampling, shading) state_dicts from an .npz with keys `sd0/<name>`, `sd1/<name>` (tests/golden/weights_pavillon.npz:
     the initialisers of sample_pavillon_16/model{0,1}.onnx, the reference's shipped trained networks)."""
@@ -56,14 +60,19 @@ def init_shading_net(input_ch=63, input_ch_views=27, W=256, D=8, skips=(4,)):
 
 
 def make_weights(kind="rand", seed=0, thr=0.2, target_spr=8.0, logits_fn=None):
-    """'rand': the reference's default init (SURVEY 8d W-rand: raw logits saturate every ray at K).
+    """'ndc': sampling net with 30 inputs (configs/fine_training_ndc.ini), last layer damped by a fixed recipe.
+    'rand': the reference's default init (SURVEY 8d W-rand: raw logits saturate every ray at K).
     'shaped': same seed, the sampling net's last layer scaled by 0.15 and its bias shifted (bisection) until the mean
     number of cells >= thr on a probe batch is ~target_spr -> ragged 1..K samples per ray (SURVEY 8d W-shaped).
     logits_fn(sd0) -> [n,128] tensor of raw sampling-net outputs on the probe batch (the caller evaluates them with the
     renderer under test)."""
     torch.manual_seed(seed)
-    sd0, sd1 = init_sampling_net(), init_shading_net()
+    sd0, sd1 = init_sampling_net(n_in=30 if kind == "ndc" else 90), init_shading_net()
     if kind == "rand":
+        return sd0, sd1
+    if kind == "ndc":   # posEncArgs "2-2" -> 30 input features; damped last layer: ragged 12..16 of K = 16 at thr 0.15
+        sd0["layers.7.weight"] = sd0["layers.7.weight"] * 0.15
+        sd0["layers.7.bias"] = sd0["layers.7.bias"] * 0.15 - 0.1
         return sd0, sd1
     if kind != "shaped":
         raise ValueError(kind)

@@ -42,6 +42,8 @@ WORKLOADS = {
     # configs[3]: one 1600x1600 frame row-tiled over the GPUs (strong scaling)
     "1600x1600_thr0.2_K8": dict(W=1600, H=1600, thr=0.2, K=8, weights="rand", scaling="strong"),
 }
+# NDC / LLFF variant (configs/fine_training_ndc.ini: 30-feature sampling net, linear depths, ndc_rays in stage 3), K = 16
+WORKLOADS["800x800_ndc_thr0.15_K16"] = dict(W=800, H=800, thr=0.15, K=16, weights="ndc", scaling="weak")
 # configs[4]: threshold sweep on the reference's shipped trained Pavillon networks (ragged at every threshold)
 for _k in (8, 16):
     for _t in (0.05, 0.1, 0.2, 0.3, 0.5):
@@ -83,7 +85,7 @@ def ncu_traffic(kernel):
         return None, tag
 
 
-def stage_rooflines(stage_ms, rays, samples, thr, peaks):
+def stage_rooflines(stage_ms, rays, samples, thr, peaks, n_feat0=90):
     """Per stage: algorithmic work / measured stage time of the profiled chunk, against the measured peak.
     `impl` = the bytes this implementation moves by construction (packed bf16 hi / lo tiles instead of fp32 rows), where it
     differs from the 8(d) figure."""
@@ -97,8 +99,8 @@ def stage_rooflines(stage_ms, rays, samples, thr, peaks):
             out[name] = dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak)
             if impl is not None:
                 out[name]["impl_bytes_frac"] = impl / (ms * 1e-3) / 1e9 / peak
-    add("stage0_features", stage_ms[0], r * (12 + 360 + 24), "GB/s", hbm, "hbm", impl=r * (12 + 512 + 24))   # 8(d): dirs in, [N,90] fp32 + ray o/d out
-    add("mlp0", stage_ms[1], r * FLOP_PER_RAY_MLP0, "TFLOP/s", peaks["tflops"], "tensor")   # algorithmic flops (x3 MMAs issued for the split)
+    add("stage0_features", stage_ms[0], r * (12 + 4 * n_feat0 + 24), "GB/s", hbm, "hbm", impl=r * (12 + 512 + 24))   # 8(d): dirs in, [N,F0] fp32 + ray o/d out
+    add("mlp0", stage_ms[1], r * (FLOP_PER_RAY_MLP0 - 2.0 * 256 * (90 - n_feat0)), "TFLOP/s", peaks["tflops"], "tensor")   # algorithmic flops (x3 MMAs issued for the split)
     if thr > 0:
         add("stage2_sample", stage_ms[2], r * (512 + 8) + m * 16, "GB/s", hbm, "hbm")
     add("stage3_posenc", stage_ms[3], m * (8 + 192) + r * 24, "GB/s", hbm, "hbm", impl=m * (8 + 256) + r * 24)   # 8(d) bf16 figure: 96 x 2 B
@@ -180,6 +182,9 @@ class CpuReference:
             from adanerf_b200 import synthetic
             self.scene = orc.SCENE_PAVILLON
             self.sd0, self.sd1 = synthetic.load_weights_npz(PAVILLON_NPZ)
+        elif cfg["weights"] == "ndc":
+            self.scene = orc.SCENE_PAVILLON_NDC
+            self.sd0, self.sd1 = orc.make_weights("ndc", seed=0)
         else:
             self.scene = orc.SCENE_BARBERSHOP
             self.sd0, self.sd1 = orc.make_weights(cfg["weights"], seed=0)
@@ -260,6 +265,10 @@ def make_renderer_inputs(cfg, torch, Renderer, synthetic, device, W, H):
     if cfg["weights"] == "pavillon":
         scene = synthetic.SCENE_PAVILLON
         sd0, sd1 = synthetic.load_weights_npz(PAVILLON_NPZ)
+        r = Renderer(scene, device=device, sampling_net=sd0, shading_net=sd1)
+    elif cfg["weights"] == "ndc":
+        scene = synthetic.SCENE_PAVILLON_NDC
+        sd0, sd1 = synthetic.make_weights("ndc", seed=0)
         r = Renderer(scene, device=device, sampling_net=sd0, shading_net=sd1)
     else:
         scene = synthetic.SCENE_BARBERSHOP
@@ -346,8 +355,12 @@ def run_ours(args, cfg, name):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    ms_by_rank = [ms / args.steps]
     if world > 1:
         t = torch.tensor([ms], device="cuda")
+        every = torch.empty(world, device="cuda")
+        dist.all_gather_into_tensor(every, t)
+        ms_by_rank = [float(x) / args.steps for x in every.tolist()]   # the spread between the GPUs of the box (power caps differ)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
@@ -439,6 +452,7 @@ def run_ours(args, cfg, name):
             rays_per_sec=rays_per_sec, samples_per_ray=float(prof_samples) / prof_rays,
             e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), api=api, finite=finite),
             gpu_launches=int(launches),
+            ms_per_step_by_rank=[round(x, 3) for x in ms_by_rank],
             clocks=clocks,
             stage_ms=dict(zip(["stage0_features", "mlp0", "stage2_sample", "stage3_posenc", "mlp1", "stage5_composite"],
                               [round(float(x), 4) for x in stage_ms])),
@@ -447,7 +461,7 @@ def run_ours(args, cfg, name):
                           frac_of_sustained=achieved / peaks["tflops_sustained"], traffic=traffic,
                           traffic_unit=f"bytes of DRAM read+write per launch (profiles/ncu_{tag}_summary.json, ncu --set full)",
                           peak_source=peaks["source"]),
-            roofline_stages=stage_rooflines(stage_ms, prof_rays, prof_samples, thr, peaks),
+            roofline_stages=stage_rooflines(stage_ms, prof_rays, prof_samples, thr, peaks, n_feat0=30 if cfg["weights"] == "ndc" else 90),
             cpu_baseline=dict(value=cpu["frames_per_s"], unit="frames/s", cores=cpu["cores"], kind="port", sample=cpu["sample"]),
         )
         print(json.dumps(line))
@@ -472,6 +486,9 @@ def run_single_process(args, cfg, name):
     if cfg["weights"] == "pavillon":
         scene = synthetic.SCENE_PAVILLON
         sd0, sd1 = synthetic.load_weights_npz(PAVILLON_NPZ)
+    elif cfg["weights"] == "ndc":
+        scene = synthetic.SCENE_PAVILLON_NDC
+        sd0, sd1 = synthetic.make_weights("ndc", seed=0)
     elif cfg["weights"] == "rand":
         scene = synthetic.SCENE_BARBERSHOP
         sd0, sd1 = synthetic.make_weights("rand", seed=0)

@@ -96,3 +96,25 @@ def test_golden_cases_meet_the_budget(case):
     print(f"{case}: identical counts {same:.4f}, PSNR {p:.2f} dB")
     assert same >= 0.999 and p >= 49.4
     r.close()
+
+
+def test_dense_rows_against_oracle(pavillon_weights, frame_dirs):
+    """BASELINE config 3 (dense, 128 samples per ray) beyond the 1024-ray golden: ten full image rows spread over the frame
+    (8000 rays, 1 024 000 samples), trained weights, rendered in several internal chunks -- against the oracle."""
+    sd0, sd1 = pavillon_weights
+    scene = orc.SCENE_PAVILLON
+    pose = torch.tensor(scene["view_cell_center"]) + POSE_OFF
+    rows = torch.arange(10) * 80 + 37
+    idx = (rows[:, None] * W + torch.arange(W)[None, :]).reshape(-1)
+    dirs = frame_dirs[idx].contiguous()
+    ref_rgb, ref_n = orc.render_frame(pose, ROT, dirs, sd0, sd1, scene, 0.0, 128, chunk=1000)
+    r = _renderer(scene, sd0, sd1)
+    r.set_option("chunk_rays", 3000)
+    out = r.render_rays(pose, ROT, dirs.cuda(), 0.0, 128)
+    rgb, n = out["rgb"].cpu(), out["n_samples"].cpu().long()
+    p = orc.psnr(rgb, ref_rgb)
+    print(f"dense K=128, {len(idx)} rays: PSNR(ours, oracle) {p:.2f} dB, max |d| {float((rgb - ref_rgb).abs().max()):.4f}")
+    assert torch.isfinite(rgb).all()
+    assert torch.equal(n, ref_n) and int(n.min()) == 128
+    assert p >= 49.4
+    r.close()
