@@ -13,7 +13,7 @@ checkpoints offline).
   e2e   : the same metric from HOST buffers to HOST buffers: ray directions start in (page-locked) host memory, the RGB
           frame ends there; at N > 1 the NCCL gather of the tiles and the D2H copy of the gathered frame are inside.
   N > 1 : default workload: weak scaling -- rank r renders rows [800 r, 800 (r+1)) of an 800 x 800N frame (640 000 rays per
-          GPU), one NCCL all-gather of the RGB tiles per frame, overlapped with the next frame (two frames in flight);
+          GPU), one NCCL gather of the RGB tiles to rank 0 per frame, left in flight under the next frame (two frames in flight);
           value = 800x800-frame equivalents per second over all ranks.  `--workload 1600x1600_thr0.2_K8` (BASELINE config
           4): STRONG scaling -- the 1600 x 1600 frame is fixed, rank r renders rows [1600 r / N, 1600 (r+1) / N).
   --single-process : N GPUs driven by ONE process through the multi-GPU C ABI (include/adanerf_b200_multi.h:
@@ -318,17 +318,28 @@ def run_ours(args, cfg, name):
     bands = [torch.empty((n_rays, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
     frames = [torch.empty((world * n_rays, 3), dtype=torch.float32, device="cuda") for _ in range(2)] if world > 1 else None
     pending = [None, None]
+    # the gathered frame as per-rank tile views (dist.gather's gather_list); A/B modes: profiles/r2/gather_ab/ (8 GPUs, weak
+    # scaling: no collective 6.62 ms, gather to rank 0 6.70, all-gather 6.80 whether left in flight or not -- NCCL's kernel and the
+    # persistent MLP kernels do not share SMs)
+    tiles = [list(f.view(world, n_rays, 3).unbind(0)) for f in frames] if world > 1 else None
+    gather_mode = os.environ.get("ADN_BENCH_GATHER", "root")
 
     def step(f):
-        """One frame: render this rank's band, then ONE NCCL all-gather of the RGB tiles, left in flight while the next frame's
-        band is rendered into the other buffer (the gather overlaps the next frame's sampling MLP)."""
+        """One frame: render this rank's band, then ONE NCCL gather of the RGB tiles to rank 0, left in flight while the next
+        frame's band is rendered into the other buffer."""
         k = f & 1
         if pending[k] is not None:
             pending[k].wait()            # the buffers of frame f - 2
             pending[k] = None
         r.render_camera(pose, rot, W, Hn, thr, K, row0=row0, rows=rows, out=bands[k])
         if world > 1:
-            pending[k] = dist.all_gather_into_tensor(frames[k], bands[k], async_op=True)
+            if gather_mode == "root":        # default: ONE NCCL gather of the tiles to rank 0 (grouped send / recv), left in flight
+                pending[k] = dist.gather(bands[k], tiles[k] if rank == 0 else None, dst=0, async_op=True)
+            elif gather_mode == "overlap":   # A/B: all-gather (every rank receives the frame), left in flight
+                pending[k] = dist.all_gather_into_tensor(frames[k], bands[k], async_op=True)
+            elif gather_mode == "sync":      # A/B: all-gather serialised behind the composite (round 1)
+                dist.all_gather_into_tensor(frames[k], bands[k])
+            # "none": no collective at all (the spread between the GPUs of the box)
 
     def drain():
         for k in range(2):
@@ -392,13 +403,13 @@ def run_ours(args, cfg, name):
         def e2e_step():
             dirs_dev.copy_(dirs_pin, non_blocking=True)
             r.render_rays(pose, rot, dirs_dev, thr, K, want_nsamples=False, out=bands[0])
-            dist.all_gather_into_tensor(frames[0], bands[0])
+            dist.gather(bands[0], tiles[0] if rank == 0 else None, dst=0)
             if rank == 0:
                 frame_pin.copy_(frames[0], non_blocking=True)
             torch.cuda.synchronize()
         result = frame_pin.numpy() if rank == 0 else None
         h2d, d2h, api = dirs_host.nbytes + 48, (world * n_rays * 12 if rank == 0 else 0), \
-            "render_rays (H2D of the band's dirs) + NCCL all-gather + D2H of the gathered frame on rank 0"
+            "render_rays (H2D of the band's dirs) + NCCL gather to rank 0 + D2H of the gathered frame"
     for _ in range(3):
         e2e_step()
     if world > 1:
@@ -448,7 +459,7 @@ def run_ours(args, cfg, name):
             warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling=cfg["scaling"], vs_baseline=None,
             dtype="bf16", data="synthetic",
             config=workload_config(name, cfg, world, n_rays, f"{W}x{Hn}", samples=prof_samples,
-                                   parallelism=f"row-bands x{world} + 1 NCCL all-gather of RGB tiles per frame (two frames in flight)"),
+                                   parallelism=f"row-bands x{world} + 1 NCCL gather of RGB tiles to rank 0 per frame (two frames in flight)" + ("" if gather_mode == "root" else f" [gather mode: {gather_mode}]")),
             rays_per_sec=rays_per_sec, samples_per_ray=float(prof_samples) / prof_rays,
             e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), api=api, finite=finite),
             gpu_launches=int(launches),
