@@ -46,7 +46,9 @@
 // cycles per N = 128 MMA are not an operand-bandwidth limit); L2 hot-spotting on the weight lines (1 / 4 / 16 / 37 replicas
 // of the blob, MlpProgram::w_copies: 4.89-4.96 ms, no change).  Measured and dropped (git history): an issue loop
 // specialised per schedule word (compile-time stages, 65 KB of code: 5.87 ms against 4.88 -- the footprint costs more
-// instruction-cache misses than the decode saved); a per-layer specialised epilogue with immediate bias operands (160 KB:
+// instruction-cache misses than the decode saved); the issuing warp software-pipelined (next step's schedule word, ring stages
+// and one non-blocking probe per barrier between the MMAs of the current step: the waits shrink from ~550 to ~400 cycles but
+// the step grows from 1350 to 2170 -- anything placed between the MMAs of a step starves the tensor queue: 6.55 ms); a per-layer specialised epilogue with immediate bias operands (160 KB:
 // 2x slower, same reason); N = 256 MMAs with alternating slots, per-slot weight passes, an early "accumulator drained"
 // signal and half-wise activation hand-off (5.3-5.7 ms).
 //
@@ -202,7 +204,6 @@ mlp_sh_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict
   uint64_t* act_ready = acc_full + 4;        // [2 g + h] leader only: both CTAs' epilogues of that half are done (TMEM drained, A blocks written)
   uint64_t* lo_free = act_ready + 4;         // [g] the blocks half 0's epilogue overwrites are no longer read by this layer's MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_free + 2);
-  uint32_t* sched_s = tmem_slot + 4;         // [48] the issue schedule, flat in issue order: word | layer << 24; [47] = steps per tile
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -228,12 +229,6 @@ mlp_sh_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < kSideFloats; i += kShThreads) side_s[i] = prog.side[i];
-  if (threadIdx.x == 32) {
-    int n = 0;
-    for (int l = 0; l < n_layers; ++l)
-      for (int i = 0; i < int(prog.sh_steps[l]) && n < 47; ++i) sched_s[n++] = prog.sh_sched[l][i] | (uint32_t(l) << 24);
-    sched_s[47] = uint32_t(n);
-  }
   if (warp == kMmaWarp) tmem_alloc_cg<2>(tmem_slot, 512);
   tc_fence_before();
   cluster_sync_all();
@@ -331,143 +326,101 @@ mlp_sh_kernel(const __grid_constant__ MlpProgram prog, const uint8_t* __restrict
     const uint32_t ring_lo = lo_of(smem_u32(ring));
     const uint32_t act_lo0 = lo_of(smem_u32(act_ptr(g, 1)));
     auto desc = [&](uint32_t lo) -> uint64_t { return desc_hi | uint64_t(lo); };
-    // Software pipeline of the issuing warp: everything step s + 1 needs (its schedule word from the shared-memory table, its
-    // ring stages, one non-blocking probe of each of its barriers, one per lane) is done BETWEEN the MMAs of step s, where
-    // the warp would otherwise sit blocked on the tensor queue (~2 MMAs deep).  At the top of a step the warp blocks only on
-    // barriers whose probe failed.
-    int stage = 0;
+    int stage = 0, in_stage = 0, in_other = 0;
     uint32_t phase = 0, ar_phase = 0;   // ar_phase: bit hh = parity of act_ready[2 g + hh]
+    bool w_seen = false;                // lane 3: the early probe has already seen this step's weight stage complete
     auto advance = [&]() {
       if (++stage == STAGES) {
         stage = 0;
         phase ^= 1;
       }
     };
-    struct StepCtx {
-      uint32_t w;                 // schedule word | layer << 24
-      int w_stage, in_stage, in_other;
-      uint32_t w_par, in_par, need;
-    };
-    const int n_flat = int(sched_s[47]);
-    // ring positions of a step: its weight stage, then (when it fetches the tile input) one stage per slot
-    auto place = [&](uint32_t w, bool act_leader, const StepCtx& prev) {
-      StepCtx c = prev;   // the input stages of a slot are fetched once per layer and used by its later steps
-      c.w = w;
-      c.need = act_leader ? ((w >> 9) & 3u) : 0u;
-      c.w_stage = stage;
-      c.w_par = phase;
-      advance();
-      if (w & (1u << 17)) {   // input stages: slot 0's, then slot 1's
-        if (g == 1) {
-          c.in_other = stage;
+    for (long long iter = 0;; ++iter) {
+      if (first_tile(iter, 0) >= n_tiles) break;
+      const bool active = first_tile(iter, g) < n_tiles;
+      for (int l = 0; l < n_layers; ++l) {
+        const int n_steps = prog.sh_steps[l];
+        uint32_t seen = 0;
+        for (int i = 0; i < n_steps; ++i) {
+          const uint32_t w = prog.sh_sched[l][i];
+          const uint32_t need = (active && leader) ? ((w >> 9) & 3u) : 0u;
+          seen |= need;
+          const int w_stage = stage;
+          const uint32_t w_par = phase;
           advance();
-        }
-        c.in_stage = stage;
-        c.in_par = phase;
-        advance();
-        if (g == 0) {
-          c.in_other = stage;
-          advance();
-        }
-      }
-      return c;
-    };
-    // the barrier lane `lane` (< 4) watches for a step: 0, 1: previous layer's half-0 / half-1 epilogue of this slot (both
-    // CTAs arrive on the leader's barrier); 2: this slot's input stage; 3: the weight stage (leader: own share + the peer's
-    // forward).  Everybody observes every weight stage: a warp that ran ahead by a full ring phase would alias the parity.
-    auto lane_bar = [&](const StepCtx& c, uint64_t*& bar, uint32_t& parity) -> bool {
-      const bool fetch = (c.w & (1u << 17)) != 0;
-      bar = lane < 2 ? &act_ready[2 * g + (lane & 1)] : (lane == 2 ? &w_full[c.in_stage] : &w_full[c.w_stage]);
-      parity = lane < 2 ? ((ar_phase >> (lane & 1)) & 1u) : (lane == 2 ? c.in_par : c.w_par);
-      return lane < 2 ? ((c.need >> lane) & 1u) != 0 : (lane == 2 ? fetch : lane == 3);
-    };
-    bool ok = false;      // this lane's barrier of the current step has been seen complete by the probe
-    int fs = 0;           // flat index of the current step
-    long long iter = 0;
-    bool active = first_tile(0, g) < n_tiles;
-    StepCtx cur = place(sched_s[0], active && leader, StepCtx{});
-    if (first_tile(0, 0) < n_tiles) {
-      for (;;) {
-        const uint32_t w = cur.w;
-        const int l = int(w >> 24);
-        const uint32_t h = (w >> 14) & 1u;
-        const bool fetch = (w & (1u << 17)) != 0;
-        if (lane == 0 && g == 0) tr(0, fs, 2 * l + int(h), 0);
-        {
-          uint64_t* bar;
-          uint32_t parity;
-          const bool needed = lane_bar(cur, bar, parity);
-          mbar_wait_lanes(bar, parity, needed && !ok, err_flag, 3);
-          if (!leader && ((lane == 2 && fetch) || (lane == 3 && g == 0))) mbar_arrive_remote(mapa_shared(smem_u32(bar), 0));
-          __syncwarp();
-          ar_phase ^= cur.need;
-        }
-        // the next step in issue order (possibly the next tile group's first)
-        const bool last_of_tile = (fs + 1 == n_flat);
-        const bool more = !last_of_tile || first_tile(iter + 1, 0) < n_tiles;
-        const bool active_nx = last_of_tile ? (first_tile(iter + 1, g) < n_tiles) : active;
-        StepCtx nxt = cur;
-        bool ok_nx = false;
-        auto prepare_next = [&]() { nxt = place(sched_s[last_of_tile ? 0 : fs + 1], active_nx && leader, cur); };
-        auto probe_next = [&]() {
-          uint64_t* bar;
-          uint32_t parity;
-          const bool needed = lane_bar(nxt, bar, parity);
-          ok_nx = (lane < 4 && needed && more) ? mbar_test(bar, parity) : false;
-        };
-        if (leader) {
-          tc_fence_after();
-          if (lane == 0 && g == 0) tr(0, g, 2 * l + int(h), (w & (1u << 15)) ? 1 : 6);
-          const uint32_t acc = ((w >> 15) & 1u) ^ 1u;   // first step of the half: overwrite
-          const uint32_t b = ring_lo + uint32_t(cur.w_stage) * (STAGE_BYTES >> 4);
-          const bool input = (w & (1u << 16)) != 0;
-          const uint32_t a0 = input ? ring_lo + uint32_t(cur.in_stage) * (STAGE_BYTES >> 4) : act_lo0 + ((w & 15u) - 1u) * (kBlkBytes >> 4);
-          const uint32_t a1 = act_lo0 + (((w >> 4) & 15u) - 1u) * (kBlkBytes >> 4);
-          const uint32_t d = tmem_base + uint32_t(g * 256) + h * 128u;
-          const bool view = (w & (1u << 19)) != 0, two = (w & (1u << 8)) != 0;
-          const bool issue = active && lane == 0;
-          if (issue) {
-            umma_bf16_cg<2>(d, desc(a0), desc(b), idesc128, acc);
-            umma_bf16_cg<2>(d, desc(a0 + 2), desc(b + 2), idesc128, 1u);
+          uint32_t in_par = 0;
+          const bool fetch = (w & (1u << 17)) != 0;
+          if (fetch) {   // input stages: slot 0's, then slot 1's
+            if (g == 1) {
+              in_other = stage;
+              advance();
+            }
+            in_stage = stage;
+            in_par = phase;
+            advance();
+            if (g == 0) {
+              in_other = stage;
+              advance();
+            }
           }
-          __syncwarp();
-          prepare_next();
-          if (issue && !view) {   // the view block carries 27 features: two K steps
-            umma_bf16_cg<2>(d, desc(a0 + 4), desc(b + 4), idesc128, 1u);
-            umma_bf16_cg<2>(d, desc(a0 + 6), desc(b + 6), idesc128, 1u);
+          if (lane == 0 && g == 0) tr(0, i, 2 * l + int((w >> 14) & 1u), 0);
+          {
+            // one barrier per lane: 0, 1: previous layer's half-0 / half-1 epilogue of this slot (both CTAs arrive on the
+            // leader's barrier); 2: this slot's input stage; 3: the weight stage (in the leader: own share + the peer's forward)
+            const bool mine = lane < 2 ? ((need >> lane) & 1u) != 0 : (lane == 2 ? fetch : (lane == 3 && !w_seen));   // everybody waits for the weight
+            // stage: a warp that ran ahead by a full ring phase would alias the parity of a later phase
+            uint64_t* bar = lane < 2 ? &act_ready[2 * g + (lane & 1)] : (lane == 2 ? &w_full[in_stage] : &w_full[w_stage]);
+            const uint32_t parity = lane < 2 ? ((ar_phase >> (lane & 1)) & 1u) : (lane == 2 ? in_par : w_par);
+            mbar_wait_lanes(bar, parity, mine, err_flag, 3);
+            if (!leader && ((lane == 2 && fetch) || (lane == 3 && g == 0))) mbar_arrive_remote(mapa_shared(smem_u32(bar), 0));
+            __syncwarp();
+            ar_phase ^= need;
           }
-          __syncwarp();
-          probe_next();
-          if (lane == 0) {
-            if (active) {
-              if (two) {
+          // Early, non-blocking probe of the NEXT step's weight stage (ring position `stage` after the advances above): its
+          // round trip overlaps the MMA issue below instead of draining the tensor pipe's short queue at the next step.
+          w_seen = (lane == 3) ? mbar_test(&w_full[stage], phase) : false;
+          if (leader) {
+            tc_fence_after();
+            if (lane == 0 && g == 0) tr(0, g, 2 * l + int((w >> 14) & 1u), (w & (1u << 15)) ? 1 : 6);
+            const uint32_t h = (w >> 14) & 1u;
+            const uint32_t acc = ((w >> 15) & 1u) ^ 1u;   // first step of the half: overwrite
+            const uint32_t b = ring_lo + uint32_t(w_stage) * (STAGE_BYTES >> 4);
+            const bool input = (w & (1u << 16)) != 0;
+            const uint32_t a0 = input ? ring_lo + uint32_t(in_stage) * (STAGE_BYTES >> 4) : act_lo0 + ((w & 15u) - 1u) * (kBlkBytes >> 4);
+            const uint32_t a1 = act_lo0 + (((w >> 4) & 15u) - 1u) * (kBlkBytes >> 4);
+            const uint32_t d = tmem_base + uint32_t(g * 256) + h * 128u;
+            if (elect_one()) {
+              if (active) {
+                umma_bf16_cg<2>(d, desc(a0), desc(b), idesc128, acc);
+                umma_bf16_cg<2>(d, desc(a0 + 2), desc(b + 2), idesc128, 1u);
+                if (!(w & (1u << 19))) {   // the view block carries 27 features: two K steps
+                  umma_bf16_cg<2>(d, desc(a0 + 4), desc(b + 4), idesc128, 1u);
+                  umma_bf16_cg<2>(d, desc(a0 + 6), desc(b + 6), idesc128, 1u);
+                }
+                if (w & (1u << 8)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_cg<2>(d, desc(a1 + 2 * k), desc(b + (HALF >> 4) + 2 * k), idesc128, 1u);
+                  for (int k = 0; k < 4; ++k) umma_bf16_cg<2>(d, desc(a1 + 2 * k), desc(b + (HALF >> 4) + 2 * k), idesc128, 1u);
+                }
+                if (w & (1u << 12)) umma_commit_cg<2>(&acc_full[2 * g + int(h)]);
+                if (w & (1u << 13)) umma_commit_cg<2>(&lo_free[g]);
               }
-              if (w & (1u << 12)) umma_commit_cg<2>(&acc_full[2 * g + int(h)]);
-              if (w & (1u << 13)) umma_commit_cg<2>(&lo_free[g]);
+              umma_commit_cg<2>(&w_empty[w_stage]);
+              if (w & (1u << 18)) {   // the tile-input stages of both slots are released here (every stage expects two commits)
+                umma_commit_cg<2>(&w_empty[in_stage]);
+                umma_commit_cg<2>(&w_empty[in_other]);
+              }
             }
-            umma_commit_cg<2>(&w_empty[cur.w_stage]);
-            if (w & (1u << 18)) {   // the tile-input stages of both slots are released here (every stage expects two commits)
-              umma_commit_cg<2>(&w_empty[cur.in_stage]);
-              umma_commit_cg<2>(&w_empty[cur.in_other]);
-            }
+            __syncwarp();
+            if (lane == 0 && g == 0 && (w & (1u << 12))) tr(0, g, 2 * l + int(h), 2);
           }
-          __syncwarp();
-          if (lane == 0 && g == 0 && (w & (1u << 12))) tr(0, g, 2 * l + int(h), 2);
-        } else {
-          prepare_next();
-          probe_next();
         }
-        if (!more) break;
-        cur = nxt;
-        ok = ok_nx;
-        active = active_nx;
-        if (last_of_tile) {
-          fs = 0;
-          ++iter;
-        } else {
-          ++fs;
+        // one completion per layer and (slot, half): consume what this layer did not need (leader only; not reached by the
+        // NeRF program, every layer of which needs both halves)
+        const uint32_t rest = (active && leader) ? (3u & ~seen) : 0u;
+        if (rest) {
+          mbar_wait_lanes(&act_ready[2 * g + (lane & 1)], (ar_phase >> (lane & 1)) & 1u, lane < 2 && ((rest >> lane) & 1u) != 0, err_flag, 9);
+          __syncwarp();
+          ar_phase ^= rest;
         }
       }
     }
