@@ -153,17 +153,16 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
-def workload_config(name, cfg, world, rays_per_gpu, frame, samples=None, parallelism=None):
-    """The `config` object both arms print (same keys, same values for the same workload)."""
-    c = dict(workload=name, frame=frame, rays_per_gpu_per_step=int(rays_per_gpu), thr=cfg["thr"], K=cfg["K"], weights=cfg["weights"],
-             scaling=cfg["scaling"],
-             l2="per-frame working set (packed features + activations I/O, >1 GB) exceeds the 126 MB L2; no explicit flush",
-             mlp0="bf16x3 split precision (fp32-class)", mlp1="bf16 operands, fp32 accumulate")
-    if samples is not None:
-        c["samples_profiled_chunk"] = int(samples)
-    if parallelism:
-        c["parallelism"] = parallelism
-    return c
+def workload_config(name, cfg, n_gpus):
+    """The `config` object: a function of (workload, number of GPUs) only, so that both arms print the same one."""
+    W, H = cfg["W"], cfg["H"]
+    strong = cfg["scaling"] == "strong"
+    Hn = H if strong else H * n_gpus
+    par = "single GPU" if n_gpus == 1 else f"row-bands x{n_gpus} + 1 NCCL gather of RGB tiles to the first GPU per frame (two frames in flight)"
+    return dict(workload=name, frame=f"{W}x{Hn}", rays_per_gpu_per_step=int(W * Hn // n_gpus), thr=cfg["thr"], K=cfg["K"], weights=cfg["weights"],
+                scaling=cfg["scaling"], parallelism=par,
+                l2="per-frame working set (packed features + activations I/O, >1 GB) exceeds the 126 MB L2; no explicit flush",
+                mlp0="bf16x3 split precision (fp32-class)", mlp1="bf16 operands, fp32 accumulate")
 
 
 # ------------------------------------------------------------------------------------------------- CPU reference arm
@@ -253,7 +252,7 @@ def run_reference(args, cfg, name):
     line = dict(impl="reference", metric=f"frames_per_sec_{cfg['W']}x{cfg['H']}", value=fps, unit="frames/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 * secs / args.steps, higher_is_better=True, scaling=cfg["scaling"],
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=workload_config(name, cfg, 1, n_frame, f"{cfg['W']}x{cfg['H']}"),
+                config=workload_config(name, cfg, args.gpus),
                 rays_per_sec=rays / secs, frames_rendered=rays / n_frame, step_is="a bounded ray sample of the frame (value = rays/s of the sample / rays per frame)",
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=last["cores"], kind="port", sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -458,8 +457,7 @@ def run_ours(args, cfg, name):
             metric=f"frames_per_sec_{W}x{H}", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
             warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling=cfg["scaling"], vs_baseline=None,
             dtype="bf16", data="synthetic",
-            config=workload_config(name, cfg, world, n_rays, f"{W}x{Hn}", samples=prof_samples,
-                                   parallelism=f"row-bands x{world} + 1 NCCL gather of RGB tiles to rank 0 per frame (two frames in flight)" + ("" if gather_mode == "root" else f" [gather mode: {gather_mode}]")),
+            config=workload_config(name, cfg, world), samples_profiled_chunk=int(prof_samples), gather_mode=gather_mode if world > 1 else None,
             rays_per_sec=rays_per_sec, samples_per_ray=float(prof_samples) / prof_rays,
             e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), api=api, finite=finite),
             gpu_launches=int(launches),
@@ -534,8 +532,7 @@ def run_single_process(args, cfg, name):
     line = dict(metric=f"frames_per_sec_{W}x{H}", value=frames_per_step * args.steps / secs, unit="frames/s", n_gpus=G, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=1000.0 * secs / args.steps, higher_is_better=True, scaling=cfg["scaling"],
                 vs_baseline=None, dtype="bf16", data="synthetic",
-                config=workload_config(name, cfg, G, rays // G, f"{W}x{Hn}",
-                                       parallelism=f"one process, {G} devices: row bands + 1 NCCL gather (grouped send/recv) per frame, two frames in flight"),
+                config=workload_config(name, cfg, G), driver="one process, all devices through include/adanerf_b200_multi.h (grouped ncclSend / ncclRecv gather)",
                 rays_per_sec=rays * args.steps / secs, timing="host clock around the pipelined loop (device work of all GPUs inside)",
                 band_ms_last_frame=[round(x, 3) for x in render_ms], gather_ms_last_frame=[round(x, 3) for x in gather_ms],
                 e2e=dict(value=frames_per_step * args.steps / e2e_s, unit="frames/s", h2d_bytes_per_step=48, d2h_bytes_per_step=rays * 12,
