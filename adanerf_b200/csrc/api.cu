@@ -59,7 +59,6 @@ struct adn_ctx {
   int64_t chunk_rays = 0;
   bool profile = false;
   int weight_copies = 1;   // replicas of each packed weight blob (MlpProgram::w_copies)
-  bool sh_refetch_inputs = true;    // mlp_sh_kernel schedule: tile inputs fetched once per N half (ADN_SH_REFETCH=0: once per layer)
   // scratch
   Buf tiles0, raw0, x0, ray_o, ray_d, dirs, count, offset, rayidx, zbuf, zpbuf, tiles1, raw1, s2scratch, rgb, rgba, x1, metric, enc_scratch;
   long long* d_total = nullptr;
@@ -446,11 +445,8 @@ adn_status build_net1(adn_ctx* ctx) {
           if (s == 0) w |= 1u << 15;
           if (!two && L.a_blk[2 * s] == 0) {   // the step's only K block is the tile input: it travels through the ring
             w |= 1u << 16;
-            if (h == 0 || ctx->sh_refetch_inputs) w |= 1u << 17;                   // fetched here (one ring stage per slot, right after the weight stage)
-            if (h == int(L.n_half) - 1 || ctx->sh_refetch_inputs) w |= 1u << 18;   // ... and released here
-            // (sh_refetch_inputs, default: the block is fetched once per N half and released right away -- two ring stages are
-            //  tied up for one step instead of until the layer's last half, at the price of a second 16 KB L2 read per slot:
-            //  +2.0 % frames/s in a same-box A/B of 3 x 60 frames each, profiles/r2/refetch_ab.txt)
+            if (h == 0) w |= 1u << 17;                        // fetched here (one ring stage per slot, right after the weight stage)
+            if (h == int(L.n_half) - 1) w |= 1u << 18;        // ... and released here
             if (L.flags & LF_WAIT_IN) w |= 1u << 19;          // view block: 27 features -> two K steps
           }
           w |= uint32_t(s) << 20;
@@ -759,7 +755,6 @@ adn_status adn_create(adn_ctx** out, const adn_scene* scene, int device) {
   ctx->num_sms = prop.multiProcessorCount;
   if (const char* cg = std::getenv("ADN_CTA_GROUP")) ctx->cta_group = (cg[0] == '1') ? 1 : 2;   // A/B experiments
   if (const char* sk = std::getenv("ADN_SHADING_KERNEL")) ctx->sh_kernel = (sk[0] != '0');
-  if (const char* rf = std::getenv("ADN_SH_REFETCH")) ctx->sh_refetch_inputs = (rf[0] != '0');
   if (const char* wc = std::getenv("ADN_WEIGHT_COPIES")) ctx->weight_copies = std::max(1, std::min(64, std::atoi(wc)));
   ctx->scene = *scene;
   if (cudaSetDevice(device) != cudaSuccess) {

@@ -4,9 +4,7 @@
 // What changed against mlp_umma_kernel<1,2,2> (which this kernel replaces for the shading net) and why:
 //   * Tile inputs (position block at layers 0 and 5, view block at the last layer) are A operands that travel through the
 //     same FIFO ring as the weights, fetched by the producer right before the step that needs them.  No resident input
-//     block per slot: the 32 KB go to the ring (5 stages of 16 KB), and the next tile's input is prefetched for free.  A block is
-//     fetched once per N half and released right after its step (holding it across the layer tied up two of the five stages
-//     for four steps: +2 % frames/s for a second 16 KB L2 read).
+//     block per slot: the 32 KB go to the ring (5 stages of 16 KB), and the next tile's input is prefetched for free.
 //   * One weight stage feeds BOTH tile slots.  The old kernel streamed every layer once per slot: 24 GB of L2 -> SM
 //     traffic per 800x800 frame (32 B / clk / SM while the tensor pipe is busy, 75 % of the measured L2 throughput),
 //     and its 4-stage ring covered only 3 x 512 tensor cycles of L2 latency -- the issue loop ran at 82 % of the pipe

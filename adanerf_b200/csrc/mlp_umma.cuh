@@ -79,7 +79,7 @@ struct MlpProgram {
   // 10: half-1 epilogue); 12 commit acc_full after this step; 13 commit lo_free; 14 N half; 15 first step of the half
   // (accumulator is overwritten, not accumulated); 16 the step's K block is the tile input (positions / view block), an
   // A operand that travels through the weight ring; 17 it is fetched at this step (two ring stages, one per slot, after
-  // the weight stage); 18 released after this step (build_net1 sets both on every input step: fetched per N half); 19 it is the view block (two K steps); 20-21 stage index in the half.
+  // the weight stage); 18 released after this step; 19 it is the view block (two K steps); 20-21 stage index in the half.
   uint32_t sh_sched[kMaxLayers][6];
   uint8_t sh_steps[kMaxLayers];
   // Biases and the two tiny heads live in the kernel parameter (constant) bank: every lane of a warp reads
