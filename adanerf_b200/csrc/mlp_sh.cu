@@ -44,7 +44,9 @@
 //     59.0 k  real epilogue, no weight traffic;      65 k  everything.
 // Ruled out by probes: the shared-memory A operand (A read from TMEM instead: 53.7 k against 53.0 k, no change -- the 91
 // cycles per N = 128 MMA are not an operand-bandwidth limit); L2 hot-spotting on the weight lines (1 / 4 / 16 / 37 replicas
-// of the blob, MlpProgram::w_copies: 4.89-4.96 ms, no change).  Measured and dropped (git history): an issue loop
+// of the blob, MlpProgram::w_copies: 4.89-4.96 ms, no change).  Measured and dropped (git history): tile inputs fetched
+// once per N half instead of once per layer (frees two of the five ring stages for four steps: +2 % frames/s in a same-box A/B,
+// but the determinism test saw frame-to-frame differences -- a race that was not found in the time left; reverted); an issue loop
 // specialised per schedule word (compile-time stages, 65 KB of code: 5.87 ms against 4.88 -- the footprint costs more
 // instruction-cache misses than the decode saved); the issuing warp software-pipelined (next step's schedule word, ring stages
 // and one non-blocking probe per barrier between the MMAs of the current step: the waits shrink from ~550 to ~400 cycles but
