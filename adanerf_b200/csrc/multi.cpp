@@ -225,16 +225,19 @@ adn_status adn_multi_render_camera(adn_multi* m, const float* pose, const float*
   }
   if (G > 1) {
     MNCCL(m, ncclGroupStart());
-    for (int r = 1; r < G; ++r) {
+    ncclResult_t res = ncclSuccess;
+    for (int r = 1; r < G && res == ncclSuccess; ++r) {
       Dev& d = m->devs[size_t(r)];
       int row0, rows;
       band_of(G, H, r, &row0, &rows);
       const size_t n = size_t(rows) * W * 3;
       if (n == 0) continue;
-      MNCCL(m, ncclSend(d.band[slot], n, ncclFloat, 0, d.comm, d.comm_s));
-      MNCCL(m, ncclRecv(m->frame[slot] + size_t(row0) * W * 3, n, ncclFloat, r, d0.comm, d0.comm_s));
+      res = ncclSend(d.band[slot], n, ncclFloat, 0, d.comm, d.comm_s);
+      if (res == ncclSuccess) res = ncclRecv(m->frame[slot] + size_t(row0) * W * 3, n, ncclFloat, r, d0.comm, d0.comm_s);
     }
-    MNCCL(m, ncclGroupEnd());
+    const ncclResult_t end = ncclGroupEnd();   // the group is closed on every path
+    if (res != ncclSuccess) return fail(m, ADN_ERR_CUDA, std::string("ncclSend / ncclRecv: ") + ncclGetErrorString(res));
+    MNCCL(m, end);
   }
   for (int r = 0; r < G; ++r) {
     Dev& d = m->devs[size_t(r)];
@@ -271,6 +274,8 @@ adn_status adn_multi_last_times(adn_multi* m, float* render_ms, float* gather_ms
     Dev& d = m->devs[r];
     MCUDA(m, cudaSetDevice(d.device));
     float a = 0.f, b = 0.f;
+    if (m->issued - m->waited >= 2)   // that slot's events have been re-recorded by the newest frame in flight
+      return fail(m, ADN_ERR_INVALID, "multi_last_times: call it before enqueuing the second next frame");
     MCUDA(m, cudaEventElapsedTime(&a, d.start[slot], d.rendered[slot]));
     MCUDA(m, cudaEventElapsedTime(&b, d.rendered[slot], d.gathered[slot]));
     if (render_ms) render_ms[r] = a;
