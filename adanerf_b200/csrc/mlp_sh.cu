@@ -46,7 +46,14 @@
 // cycles per N = 128 MMA are not an operand-bandwidth limit); L2 hot-spotting on the weight lines (1 / 4 / 16 / 37 replicas
 // of the blob, MlpProgram::w_copies: 4.89-4.96 ms, no change).  Measured and dropped (git history): tile inputs fetched
 // once per N half instead of once per layer (frees two of the five ring stages for four steps: +2 % frames/s in a same-box A/B,
-// but the determinism test saw frame-to-frame differences -- a race that was not found in the time left; reverted); an issue loop
+// but the determinism test saw frame-to-frame differences; reverted.  Cause, found afterwards on paper: an issuer commits the
+// release of the OTHER slot's input stage (`in_other`) without ever having observed that stage's `w_full`, so its arrival for
+// pass n + 1 of that ring stage can reach `w_empty` before the other issuer's arrival for pass n -- the phase then completes
+// on two arrivals of the same warp and the producer refills a stage the other slot's MMAs still read.  With the release in
+// the fetch step this needs a lag of less than one step between the issuers; in the shipped schedule only the last layer's
+// view block is released in its fetch step and the lag needed is three steps (> 3000 cycles, never seen: 0 differing frames
+// in profiles/determinism_stress.py).  Fix to apply with a GPU at hand: at fetch steps let a fifth lane of each leader issuer
+// wait for `w_full[in_other]` as well before the step's commits); an issue loop
 // specialised per schedule word (compile-time stages, 65 KB of code: 5.87 ms against 4.88 -- the footprint costs more
 // instruction-cache misses than the decode saved); the issuing warp software-pipelined (next step's schedule word, ring stages
 // and one non-blocking probe per barrier between the MMAs of the current step: the waits shrink from ~550 to ~400 cycles but
