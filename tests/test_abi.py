@@ -72,3 +72,21 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_build_is_idempotent_and_content_keyed():
+    """build() decides by the content hash of the sources (sidecar .srchash), not by mtimes: calling it again -- or after a
+    copy of the tree that touched every file -- must not start a compiler."""
+    import os
+    import __graft_entry__ as ge
+    ge.build()
+    before = {p: os.path.getmtime(p) for p in (ge.LIB, ge.MULTI_LIB, ge.VIEWER)}
+    src = os.path.join(ge.CSRC, "api.cu")
+    st = os.stat(src)
+    try:
+        os.utime(src, None)          # "newer than the library" by mtime
+        ge.build()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    assert before == {p: os.path.getmtime(p) for p in before}
+    assert not ge._stale(ge.LIB, ge.SOURCES + ge.HEADERS)
